@@ -1,0 +1,186 @@
+/* pcgc.h -- C ABI of libpcgc: the B200-native (sm_100a) hot path of the PCGCv2
+ * multiscale sparse-conv point-cloud geometry codec.
+ *
+ * The reference (NJUVISION/PCGCv2) has no C ABI of its own: its hot path lives
+ * in the third-party MinkowskiEngine / torchac packages, entered from Python.
+ * Each entry point below names the reference call site whose native work it
+ * replaces (file:line in the reference repository) and the SURVEY.md section 8
+ * row it implements.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - no allocation inside: callers pass outputs and (where needed) a workspace
+ *     whose size comes from the matching *_ws_bytes() query;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     calls are asynchronous on that stream unless stated otherwise;
+ *   - return value: 0 = ok, <0 = error, text via pcgc_last_error() (thread
+ *     local); no exception crosses the boundary;
+ *   - coordinate KEYS: uint64 = (batch << 57) | morton3(x, y, z) of the
+ *     coordinate divided by the tensor stride (x in the lowest bit of each
+ *     triple), 19 bits per axis, batch < 127.  One level up the octree shifts
+ *     the 57-bit Morton field right by 3 (batch bits stay); the child index k
+ *     (= ix + 2*iy + 4*iz, the reference's kernel index for k=2 kernels) is
+ *     key & 7.  PCGC_EMPTY_KEY marks a free hash slot.
+ */
+#ifndef PCGC_H_
+#define PCGC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCGC_OK 0
+#define PCGC_ERR_INVALID (-1)
+#define PCGC_ERR_CUDA (-2)
+#define PCGC_ERR_WORKSPACE (-3)
+#define PCGC_ERR_RANGE (-4)
+#define PCGC_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define PCGC_MAX_COORD ((1 << 19) - 1)
+#define PCGC_MAX_BATCH 126
+
+/* epilogue flags of the convolution entry points */
+#define PCGC_EPI_RELU 1       /* out = max(out, 0) after bias (+ residual) */
+
+int pcgc_version(void);
+const char *pcgc_last_error(void);
+/* number of kernels libpcgc has launched in this process (bench.py's gpu_launches) */
+uint64_t pcgc_launch_count(void);
+
+/* ---- coordinates ------------------- */
+
+/* a1  ME.SparseTensor(features, coordinates, tensor_stride) -- data_utils.py:96,108,116,
+ * coder.py:102.  coords int32 [n,4] = (b,x,y,z), every spatial entry a multiple of
+ * tensor_stride.  err_flag (device int32, caller zeroes it) is set to 1 on a
+ * coordinate outside [0, PCGC_MAX_COORD*stride], a batch > PCGC_MAX_BATCH or a
+ * non-multiple of the stride. */
+int pcgc_pack_keys(const int32_t *coords, int64_t n, int32_t tensor_stride, uint64_t *keys,
+                   int32_t *err_flag, void *stream);
+int pcgc_unpack_keys(const uint64_t *keys, int64_t n, int32_t tensor_stride, int32_t *coords,
+                     void *stream);
+
+/* capacity (slots, a power of two >= 2n) of the hash table for n keys */
+int64_t pcgc_hash_capacity(int64_t n);
+/* a1  coordinate-map insertion.  Fills table_keys[cap] / table_vals[cap] (cleared here)
+ * with key -> smallest row holding it; n_dup (device int32) receives the number of
+ * rows whose key was already present (0 = all rows unique). */
+int pcgc_hash_build(const uint64_t *keys, int64_t n, uint64_t *table_keys, int32_t *table_vals,
+                    int64_t cap, int32_t *n_dup, void *stream);
+/* first-seen flags for de-duplication (A.2): keep[i] = 1 iff row i is the
+ * representative of its key in the table built by pcgc_hash_build. */
+int pcgc_hash_keep_flags(const uint64_t *keys, int64_t n, const uint64_t *table_keys,
+                         const int32_t *table_vals, int64_t cap, uint8_t *keep, void *stream);
+/* a11 isin(data.C, gt.C) -- data_utils.py:63-75.  found[i] = 1 iff query key i is in the table. */
+int pcgc_hash_contains(const uint64_t *query, int64_t n, const uint64_t *table_keys, int64_t cap,
+                       uint8_t *found, void *stream);
+
+/* a4  kernel map of a k=3 stride-1 convolution (coordinate_manager.kernel_map behind every
+ * k=3 ME.MinkowskiConvolution in autoencoder.py:13,20,35,71,90,109,128,162,...).
+ * nbr int32 [27][n] (offset-major): nbr[k*n + u] = row of coords[u] + offset_k or -1,
+ * k = ix + 3*iy + 9*iz, offsets {-1,0,1} * tensor_stride, x fastest.  n_pairs (device
+ * int64, may be NULL) receives the number of (in,out) pairs. */
+int pcgc_kernel_map_k3(const uint64_t *keys, int64_t n, const uint64_t *table_keys,
+                       const int32_t *table_vals, int64_t cap, int32_t *nbr,
+                       unsigned long long *n_pairs, void *stream);
+
+/* a5  output coordinate map + kernel map of ME.MinkowskiConvolution(kernel_size=2, stride=2)
+ * -- autoencoder.py:78,97,116.  Parents = unique(parent(key)) in ascending key order.
+ * Outputs: parent_keys[<=n], n_parents (device int32), child_rows int32 [n] (input rows
+ * grouped by parent, ascending child index), child_off int32 [n_parents+1] (CSR offsets
+ * into child_rows; caller provides n+1 entries).  keys_are_sorted != 0 promises ascending
+ * keys (the order every map derived by this library has) and skips the radix sort. */
+size_t pcgc_stride_down_ws_bytes(int64_t n);
+int pcgc_stride_down(const uint64_t *keys, int64_t n, int32_t keys_are_sorted, uint64_t *parent_keys,
+                     int32_t *n_parents, int32_t *child_rows, int32_t *child_off, void *ws,
+                     size_t ws_bytes, void *stream);
+
+/* a6  output coordinate map of ME.MinkowskiGenerativeConvolutionTranspose(k=2, s=2)
+ * -- autoencoder.py:155,182,209: child_keys[8*i + k] = child(keys[i], k) (Morton field << 3 | k). */
+int pcgc_upsample_keys(const uint64_t *keys, int64_t n, uint64_t *child_keys, void *stream);
+
+/* generic helpers: exclusive scan of a uint8 mask and stable argsort of uint64 keys
+ * (a10 sort_spare_tensor -- data_utils.py:91-101, coder.py:97-99). */
+size_t pcgc_argsort_ws_bytes(int64_t n);
+int pcgc_argsort_u64(const uint64_t *keys, int64_t n, int end_bit, uint64_t *keys_sorted,
+                     int32_t *order, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- convolutions (rows a3, a5, a6, a7) -------------------------------------------------
+ * Features are float32 row-major with an explicit leading dimension (ld, in floats) so a
+ * layer can read/write a column slice of a wider tensor (ME.cat fusion): element (r, c) of
+ * a tensor is base[r*ld + c].  weight is the reference parameter `kernel` [K][cin][cout]
+ * (2-D [cin][cout] for K = 1), bias is `bias` [1][cout] or NULL.  residual (may be NULL)
+ * is added before the optional ReLU: out = epi(conv + bias + residual). */
+
+/* a3  ME.MinkowskiConvolution(kernel_size=3, stride=1).forward.  nbr from pcgc_kernel_map_k3. */
+int pcgc_conv_k3_fwd(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, const float *weight,
+                     const float *bias, int32_t cin, int32_t cout, const float *residual,
+                     int32_t res_ld, float *out, int32_t out_ld, int32_t flags, void *stream);
+/* a7  ME.MinkowskiConvolution(kernel_size=1) == F.mm(kernel) + bias. */
+int pcgc_conv_k1_fwd(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias,
+                     int32_t cin, int32_t cout, const float *residual, int32_t res_ld, float *out,
+                     int32_t out_ld, int32_t flags, void *stream);
+/* a5  ME.MinkowskiConvolution(kernel_size=2, stride=2).forward: out[p] = b + sum over the
+ * children j of p of in[child_rows[j]] @ W[child_k[j]], child_k = in_keys[row] & 7. */
+int pcgc_conv_k2s2_fwd(const float *in, int32_t in_ld, const uint64_t *in_keys, const int32_t *child_rows,
+                       const int32_t *child_off, int64_t n_parents, const float *weight, const float *bias,
+                       int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, void *stream);
+/* a6  ME.MinkowskiGenerativeConvolutionTranspose(kernel_size=2, stride=2).forward:
+ * out[8*i + k] = in[i] @ W[k] + bias. */
+int pcgc_convT_k2s2_fwd(const float *in, int32_t in_ld, int64_t n_in, const float *weight, const float *bias,
+                        int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, void *stream);
+
+/* ---- selection / pruning (rows a8, a9) --------------------------------------------------- */
+
+/* a9  istopk -- data_utils.py:77-89 (torch.topk on the CPU in the reference): mask[i] = 1 on
+ * the k largest logits (stride ld floats apart); ties at the threshold resolve to the lowest rows. */
+size_t pcgc_topk_mask_ws_bytes(int64_t n);
+int pcgc_topk_mask(const float *logits, int32_t ld, int64_t n, int64_t k, uint8_t *mask, void *ws,
+                   size_t ws_bytes, void *stream);
+/* a8  ME.MinkowskiPruning()(x, mask) -- autoencoder.py:237,247: stable compaction of keys and
+ * feature rows; n_kept (device int32) receives the count. */
+size_t pcgc_prune_ws_bytes(int64_t n);
+int pcgc_prune(const uint8_t *mask, int64_t n, const uint64_t *keys, const float *feats, int32_t ld,
+               int32_t channels, uint64_t *keys_out, float *feats_out, int32_t out_ld, int32_t *n_kept,
+               void *ws, size_t ws_bytes, void *stream);
+
+/* ---- entropy bottleneck (rows a12, a13, a14) ---------------------------------------------
+ * params: the 12 reference tensors entropy_bottleneck._matrices.0..3, _biases.0..3,
+ * _factors.0..3 packed per channel as 44 floats (+4 pad = 48):
+ *   [M0(3) M1(9, [out][in]) M2(9) M3(3) | B0(3) B1(3) B2(3) B3(1) | F0(3) F1(3) F2(3) F3(1)]
+ * (raw values; softplus / tanh are applied inside, entropy_model.py:95-99). */
+#define PCGC_EB_PARAMS_PER_CHANNEL 48
+/* a12 EntropyBottleneck._likelihood -- entropy_model.py:112-130.  values/lik float32 [n][c]. */
+int pcgc_eb_likelihood_fwd(const float *values, int64_t n, int32_t channels, const float *params,
+                           float *likelihood, void *stream);
+/* a13/a14 table of compress()/decompress() -- entropy_model.py:155-171,181-189: for symbols
+ * min_v..max_v: pmf = max(likelihood, 1e-9); cdf = clamp(cumsum, max=1) with a leading 0
+ * -> cdf_float [c][L+1]; cdf_u16 (may be NULL) the torchac integer table (Appendix B.1). */
+int pcgc_eb_cdf_table(const float *params, int32_t channels, int32_t min_v, int32_t max_v,
+                      float *cdf_float, uint16_t *cdf_u16, void *stream);
+/* a13 quantiser of compress() -- entropy_model.py:152-163: minmax (device int32[2], caller
+ * initialises to {INT32_MAX, INT32_MIN}) gets min/max of round(feats); second call writes
+ * sym = round(feats) - min as int16. */
+int pcgc_eb_round_minmax(const float *feats, int64_t count, int32_t *minmax, void *stream);
+int pcgc_eb_symbols(const float *feats, int64_t count, const int32_t *minmax, int16_t *sym, void *stream);
+
+/* ---- range coder (row a15; HOST functions, synchronous) ----------------------------------
+ * torchac.encode_float_cdf / decode_float_cdf -- entropy_model.py:174,192.
+ * cdf_float_host: float32 [n_tables][lp]; symbol i is coded with table row (i % n_tables)
+ * (n_tables = channels for the reference's tiled table, = n_sym for per-symbol rows).
+ * encode returns the byte count (writes at most cap bytes) or <0. */
+int64_t pcgc_rc_encode_host(const float *cdf_float_host, int64_t n_tables, int32_t lp,
+                            const int16_t *sym_host, int64_t n_sym, uint8_t *out_host, int64_t cap);
+int pcgc_rc_decode_host(const float *cdf_float_host, int64_t n_tables, int32_t lp, const uint8_t *in_host,
+                        int64_t in_len, int16_t *sym_host, int64_t n_sym);
+/* same with a ready uint16 table [n_tables][lp] */
+int64_t pcgc_rc_encode_u16_host(const uint16_t *cdf_u16_host, int64_t n_tables, int32_t lp,
+                                const int16_t *sym_host, int64_t n_sym, uint8_t *out_host, int64_t cap);
+int pcgc_rc_decode_u16_host(const uint16_t *cdf_u16_host, int64_t n_tables, int32_t lp,
+                            const uint8_t *in_host, int64_t in_len, int16_t *sym_host, int64_t n_sym);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCGC_H_ */

@@ -1,0 +1,102 @@
+"""ctypes binding of libpcgc.so (the C ABI declared in include/pcgc.h).
+
+The library is the product: nothing here falls back to a CPU implementation.  A
+missing library raises ``PcgcLibraryError`` with the build command; a failed
+call raises ``PcgcError`` carrying ``pcgc_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpcgc.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+
+class PcgcLibraryError(RuntimeError):
+    pass
+
+
+class PcgcError(RuntimeError):
+    pass
+
+
+c_p = ctypes.c_void_p
+c_i32 = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/pcgc.h one to one
+SIGNATURES = {
+    "pcgc_version": (ctypes.c_int, []),
+    "pcgc_last_error": (ctypes.c_char_p, []),
+    "pcgc_launch_count": (ctypes.c_uint64, []),
+    "pcgc_pack_keys": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p]),
+    "pcgc_unpack_keys": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p]),
+    "pcgc_hash_capacity": (c_i64, [c_i64]),
+    "pcgc_hash_build": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p]),
+    "pcgc_hash_keep_flags": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p]),
+    "pcgc_hash_contains": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p]),
+    "pcgc_kernel_map_k3": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_p]),
+    "pcgc_stride_down_ws_bytes": (c_sz, [c_i64]),
+    "pcgc_stride_down": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "pcgc_upsample_keys": (ctypes.c_int, [c_p, c_i64, c_p, c_p]),
+    "pcgc_argsort_ws_bytes": (c_sz, [c_i64]),
+    "pcgc_argsort_u64": (ctypes.c_int, [c_p, c_i64, ctypes.c_int, c_p, c_p, c_p, c_sz, c_p]),
+    "pcgc_conv_k3_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),
+    "pcgc_conv_k1_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),
+    "pcgc_conv_k2s2_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_i32, c_p]),
+    "pcgc_convT_k2s2_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_i32, c_p]),
+    "pcgc_topk_mask_ws_bytes": (c_sz, [c_i64]),
+    "pcgc_topk_mask": (ctypes.c_int, [c_p, c_i32, c_i64, c_i64, c_p, c_p, c_sz, c_p]),
+    "pcgc_prune_ws_bytes": (c_sz, [c_i64]),
+    "pcgc_prune": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_p, c_i32, c_p, c_p, c_sz, c_p]),
+    "pcgc_eb_likelihood_fwd": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p]),
+    "pcgc_eb_cdf_table": (ctypes.c_int, [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p]),
+    "pcgc_eb_round_minmax": (ctypes.c_int, [c_p, c_i64, c_p, c_p]),
+    "pcgc_eb_symbols": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_p]),
+    "pcgc_rc_encode_host": (c_i64, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
+    "pcgc_rc_decode_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
+    "pcgc_rc_encode_u16_host": (c_i64, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
+    "pcgc_rc_decode_u16_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
+}
+
+_lib = None
+
+
+def build(jobs: int = 8, verbose: bool = False) -> str:
+    """Compile libpcgc.so in-tree with nvcc for sm_100a (see csrc/Makefile)."""
+    cmd = ["make", "-C", CSRC, f"-j{jobs}"]
+    res = subprocess.run(cmd, capture_output=not verbose, text=True)
+    if res.returncode != 0:
+        raise PcgcLibraryError("building libpcgc.so failed:\n" + (res.stdout or "") + (res.stderr or ""))
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PcgcLibraryError(
+                f"{LIB_PATH} is missing: build it with `make -C {CSRC}` (or __graft_entry__.build()); "
+                "there is no CPU fallback")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the ABI and the binding diverge
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "pcgc"):
+    if rc < 0:
+        raise PcgcError(f"{what} failed ({rc}): {lib().pcgc_last_error().decode(errors='replace')}")
+    return rc
+
+
+def launch_count() -> int:
+    return int(lib().pcgc_launch_count())

@@ -1,0 +1,154 @@
+// conv.cu -- C-ABI entry points + kernel dispatch for the sparse convolutions
+// (SURVEY section 8 rows a3, a5, a6, a7).
+#include "common.cuh"
+#include "conv_dispatch.h"
+
+namespace pcgc {
+
+// generic fallback for channel counts the specialised kernels do not cover (correct, slow):
+// one thread per (row, output channel), weights from global memory.
+__global__ void conv_generic_kernel(const float *__restrict__ in, int in_ld, const int32_t *__restrict__ nbr,
+                                    int64_t n, int kvol, const float *__restrict__ weight,
+                                    const float *__restrict__ bias, int cin, int cout,
+                                    const float *__restrict__ residual, int res_ld, float *__restrict__ out,
+                                    int out_ld, int flags) {
+    const int64_t total = n * cout;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / cout;
+        const int co = (int)(i % cout);
+        float acc = 0.f;
+        for (int k = 0; k < kvol; ++k) {
+            const int64_t src = nbr ? nbr[(int64_t)k * n + row] : row;
+            if (src < 0) continue;
+            const float *x = in + src * in_ld;
+            const float *w = weight + ((int64_t)k * cin) * cout + co;
+            for (int ci = 0; ci < cin; ++ci) acc = fmaf(x[ci], w[(int64_t)ci * cout], acc);
+        }
+        if (bias) acc += bias[co];
+        if (residual) acc += residual[row * res_ld + co];
+        if (flags & PCGC_EPI_RELU) acc = fmaxf(acc, 0.f);
+        out[row * out_ld + co] = acc;
+    }
+}
+
+__global__ void conv_down_generic_kernel(const float *__restrict__ in, int in_ld, const uint64_t *__restrict__ in_keys,
+                                         const int32_t *__restrict__ child_rows, const int32_t *__restrict__ child_off,
+                                         int64_t n_parents, const float *__restrict__ weight,
+                                         const float *__restrict__ bias, int cin, int cout, float *__restrict__ out,
+                                         int out_ld, int flags) {
+    const int64_t total = n_parents * cout;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / cout;
+        const int co = (int)(i % cout);
+        float acc = 0.f;
+        for (int j = child_off[row]; j < child_off[row + 1]; ++j) {
+            const int64_t src = child_rows[j];
+            const int k = (int)(in_keys[src] & 7);
+            const float *x = in + src * in_ld;
+            const float *w = weight + ((int64_t)k * cin) * cout + co;
+            for (int ci = 0; ci < cin; ++ci) acc = fmaf(x[ci], w[(int64_t)ci * cout], acc);
+        }
+        if (bias) acc += bias[co];
+        if (flags & PCGC_EPI_RELU) acc = fmaxf(acc, 0.f);
+        out[row * out_ld + co] = acc;
+    }
+}
+
+__global__ void conv_up_generic_kernel(const float *__restrict__ in, int in_ld, int64_t n_in,
+                                       const float *__restrict__ weight, const float *__restrict__ bias, int cin,
+                                       int cout, float *__restrict__ out, int out_ld, int flags) {
+    const int64_t total = n_in * 8 * cout;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t orow = i / cout;
+        const int co = (int)(i % cout);
+        const int k = (int)(orow & 7);
+        const float *x = in + (orow >> 3) * in_ld;
+        const float *w = weight + ((int64_t)k * cin) * cout + co;
+        float acc = 0.f;
+        for (int ci = 0; ci < cin; ++ci) acc = fmaf(x[ci], w[(int64_t)ci * cout], acc);
+        if (bias) acc += bias[co];
+        if (flags & PCGC_EPI_RELU) acc = fmaxf(acc, 0.f);
+        out[orow * out_ld + co] = acc;
+    }
+}
+
+}  // namespace pcgc
+
+using namespace pcgc;
+
+static int check_conv_args(const char *who, const void *in, const void *w, const void *out, int64_t n, int cin, int cout,
+                           int in_ld, int out_ld) {
+    PCGC_REQUIRE(n >= 0 && cin >= 1 && cout >= 1 && in_ld >= cin && out_ld >= cout,
+                 "%s: bad shape n=%lld cin=%d cout=%d ld=%d/%d", who, (long long)n, cin, cout, in_ld, out_ld);
+    PCGC_REQUIRE(n == 0 || (in && w && out), "%s: null pointer", who);
+    return PCGC_OK;
+}
+
+extern "C" {
+
+int pcgc_conv_k3_fwd(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, const float *weight,
+                     const float *bias, int32_t cin, int32_t cout, const float *residual, int32_t res_ld, float *out,
+                     int32_t out_ld, int32_t flags, void *stream) {
+    int rc = check_conv_args("pcgc_conv_k3_fwd", in, weight, out, n, cin, cout, in_ld, out_ld);
+    if (rc || n == 0) return rc;
+    PCGC_REQUIRE(nbr != nullptr, "pcgc_conv_k3_fwd: null kernel map");
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = kNotHandled;
+#define CASE(CI) if (cin == CI) rc = k3_ci##CI(in, in_ld, nbr, n, weight, bias, cout, residual, res_ld, out, out_ld, flags, s);
+    PCGC_FOR_CI(CASE)
+#undef CASE
+    if (rc != kNotHandled) return rc;
+    conv_generic_kernel<<<grid_for(n * cout, 256, 8), 256, 0, s>>>(in, in_ld, nbr, n, 27, weight, bias, cin, cout,
+                                                                   residual, res_ld, out, out_ld, flags);
+    return check_launch("conv_generic");
+}
+
+int pcgc_conv_k1_fwd(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias, int32_t cin,
+                     int32_t cout, const float *residual, int32_t res_ld, float *out, int32_t out_ld, int32_t flags,
+                     void *stream) {
+    int rc = check_conv_args("pcgc_conv_k1_fwd", in, weight, out, n, cin, cout, in_ld, out_ld);
+    if (rc || n == 0) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = kNotHandled;
+#define CASE(CI) if (cin == CI) rc = k1_ci##CI(in, in_ld, n, weight, bias, cout, residual, res_ld, out, out_ld, flags, s);
+    PCGC_FOR_CI(CASE)
+#undef CASE
+    if (rc != kNotHandled) return rc;
+    conv_generic_kernel<<<grid_for(n * cout, 256, 8), 256, 0, s>>>(in, in_ld, nullptr, n, 1, weight, bias, cin, cout,
+                                                                   residual, res_ld, out, out_ld, flags);
+    return check_launch("conv_generic");
+}
+
+int pcgc_conv_k2s2_fwd(const float *in, int32_t in_ld, const uint64_t *in_keys, const int32_t *child_rows,
+                       const int32_t *child_off, int64_t n_parents, const float *weight, const float *bias,
+                       int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, void *stream) {
+    int rc = check_conv_args("pcgc_conv_k2s2_fwd", in, weight, out, n_parents, cin, cout, in_ld, out_ld);
+    if (rc || n_parents == 0) return rc;
+    PCGC_REQUIRE(in_keys && child_rows && child_off, "pcgc_conv_k2s2_fwd: null map");
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = kNotHandled;
+#define CASE(CI) if (cin == CI) rc = down_ci##CI(in, in_ld, in_keys, child_rows, child_off, n_parents, weight, bias, cout, out, out_ld, flags, s);
+    PCGC_FOR_CI(CASE)
+#undef CASE
+    if (rc != kNotHandled) return rc;
+    conv_down_generic_kernel<<<grid_for(n_parents * cout, 256, 8), 256, 0, s>>>(
+        in, in_ld, in_keys, child_rows, child_off, n_parents, weight, bias, cin, cout, out, out_ld, flags);
+    return check_launch("conv_down_generic");
+}
+
+int pcgc_convT_k2s2_fwd(const float *in, int32_t in_ld, int64_t n_in, const float *weight, const float *bias,
+                        int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, void *stream) {
+    int rc = check_conv_args("pcgc_convT_k2s2_fwd", in, weight, out, n_in, cin, cout, in_ld, out_ld);
+    if (rc || n_in == 0) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = kNotHandled;
+#define CASE(CI) if (cin == CI) rc = up_ci##CI(in, in_ld, n_in, weight, bias, cout, out, out_ld, flags, s);
+    PCGC_FOR_CI(CASE)
+#undef CASE
+    if (rc != kNotHandled) return rc;
+    conv_up_generic_kernel<<<grid_for(n_in * 8 * cout, 256, 8), 256, 0, s>>>(in, in_ld, n_in, weight, bias, cin, cout,
+                                                                            out, out_ld, flags);
+    return check_launch("conv_up_generic");
+}
+
+}  // extern "C"

@@ -1,0 +1,337 @@
+"""Host-side operators over libpcgc (C ABI in include/pcgc.h).
+
+PyTorch is used for device memory, streams and the caching allocator only; every
+computation below is a call into the hand-written sm_100a kernels.  Keys are kept
+in ``torch.int64`` tensors holding the uint64 bit pattern described in pcgc.h.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+EPI_RELU = 1
+EB_PPC = 48
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("pcgcv2_b200 operators run on CUDA tensors only (there is no CPU path)")
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------ coordinates
+
+def pack_keys(coords: torch.Tensor, tensor_stride: int) -> torch.Tensor:
+    """int32 [N,4] (b,x,y,z) -> int64 [N] Morton keys (validates range; one sync)."""
+    _need_cuda(coords)
+    if coords.dtype != torch.int32:
+        raise ValueError("coordinates must be int32")
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    keys = torch.empty(n, dtype=torch.int64, device=coords.device)
+    err = torch.zeros(1, dtype=torch.int32, device=coords.device)
+    check(_lib.lib().pcgc_pack_keys(_p(coords), n, int(tensor_stride), _p(keys), _p(err), _stream()), "pcgc_pack_keys")
+    if n and int(err.item()):
+        raise ValueError("coordinates out of range: need 0 <= c/stride <= %d, batch <= 126, c %% stride == 0"
+                         % ((1 << 19) - 1))
+    return keys
+
+
+def unpack_keys(keys: torch.Tensor, tensor_stride: int) -> torch.Tensor:
+    n = keys.shape[0]
+    coords = torch.empty((n, 4), dtype=torch.int32, device=keys.device)
+    check(_lib.lib().pcgc_unpack_keys(_p(keys), n, int(tensor_stride), _p(coords), _stream()), "pcgc_unpack_keys")
+    return coords
+
+
+class HashTable:
+    """key -> row table of one coordinate map."""
+
+    def __init__(self, keys: torch.Tensor):
+        n = keys.shape[0]
+        L = _lib.lib()
+        self.cap = int(L.pcgc_hash_capacity(n))
+        self.tkeys = torch.empty(self.cap, dtype=torch.int64, device=keys.device)
+        self.tvals = torch.empty(self.cap, dtype=torch.int32, device=keys.device)
+        self._ndup = torch.zeros(1, dtype=torch.int32, device=keys.device)
+        check(L.pcgc_hash_build(_p(keys), n, _p(self.tkeys), _p(self.tvals), self.cap, _p(self._ndup), _stream()),
+              "pcgc_hash_build")
+
+    @property
+    def n_dup(self) -> int:
+        return int(self._ndup.item())
+
+    def keep_flags(self, keys):
+        keep = torch.empty(keys.shape[0], dtype=torch.uint8, device=keys.device)
+        check(_lib.lib().pcgc_hash_keep_flags(_p(keys), keys.shape[0], _p(self.tkeys), _p(self.tvals), self.cap,
+                                              _p(keep), _stream()), "pcgc_hash_keep_flags")
+        return keep
+
+    def contains(self, query):
+        found = torch.empty(query.shape[0], dtype=torch.uint8, device=query.device)
+        check(_lib.lib().pcgc_hash_contains(_p(query), query.shape[0], _p(self.tkeys), self.cap, _p(found), _stream()),
+              "pcgc_hash_contains")
+        return found.bool()
+
+
+def kernel_map_k3(keys: torch.Tensor, table: HashTable, count_pairs=False):
+    """-> nbr int32 [27, N] (offset-major, -1 = missing) [, device int64 pair count]."""
+    n = keys.shape[0]
+    nbr = torch.empty((27, n), dtype=torch.int32, device=keys.device)
+    npairs = torch.zeros(1, dtype=torch.int64, device=keys.device) if count_pairs else None
+    check(_lib.lib().pcgc_kernel_map_k3(_p(keys), n, _p(table.tkeys), _p(table.tvals), table.cap, _p(nbr), _p(npairs),
+                                        _stream()), "pcgc_kernel_map_k3")
+    return (nbr, npairs) if count_pairs else nbr
+
+
+def stride_down(keys: torch.Tensor, keys_are_sorted=False):
+    """-> (parent_keys [P], child_rows int32 [N], child_off int32 [P+1]); one sync for P."""
+    n = keys.shape[0]
+    L = _lib.lib()
+    dev = keys.device
+    parent = torch.empty(n, dtype=torch.int64, device=dev)
+    n_par = torch.zeros(1, dtype=torch.int32, device=dev)
+    rows = torch.empty(n, dtype=torch.int32, device=dev)
+    off = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    nbytes = L.pcgc_stride_down_ws_bytes(n)
+    ws = _ws(nbytes, dev)
+    check(L.pcgc_stride_down(_p(keys), n, int(bool(keys_are_sorted)), _p(parent), _p(n_par), _p(rows), _p(off), _p(ws),
+                             nbytes, _stream()), "pcgc_stride_down")
+    p = int(n_par.item())
+    return parent[:p], rows, off[:p + 1]
+
+
+def upsample_keys(keys: torch.Tensor) -> torch.Tensor:
+    n = keys.shape[0]
+    out = torch.empty(8 * n, dtype=torch.int64, device=keys.device)
+    check(_lib.lib().pcgc_upsample_keys(_p(keys), n, _p(out), _stream()), "pcgc_upsample_keys")
+    return out
+
+
+def argsort_u64(keys: torch.Tensor, end_bit=64):
+    """stable ascending argsort of uint64 bit patterns -> (sorted keys, order int32)."""
+    n = keys.shape[0]
+    L = _lib.lib()
+    ks = torch.empty_like(keys)
+    order = torch.empty(n, dtype=torch.int32, device=keys.device)
+    nbytes = L.pcgc_argsort_ws_bytes(n)
+    ws = _ws(nbytes, keys.device)
+    check(L.pcgc_argsort_u64(_p(keys), n, int(end_bit), _p(ks), _p(order), _p(ws), nbytes, _stream()), "pcgc_argsort_u64")
+    return ks, order
+
+
+# ------------------------------------------------------------------ convolutions
+
+def _feat(t):
+    _need_cuda(t)
+    if t.dtype != torch.float32:
+        raise ValueError("features must be float32")
+    if t.dim() != 2 or t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _out_slice(out, n, cout, device):
+    if out is None:
+        out = torch.empty((n, cout), dtype=torch.float32, device=device)
+    assert out.shape[0] == n and out.shape[1] == cout and out.stride(1) == 1
+    return out
+
+
+def conv_k3(feats, nbr, weight, bias=None, residual=None, relu=False, out=None):
+    feats = _feat(feats)
+    n, cin = feats.shape
+    cout = weight.shape[2]
+    assert weight.shape[0] == 27 and weight.shape[1] == cin and weight.is_contiguous()
+    out = _out_slice(out, n, cout, feats.device)
+    residual = None if residual is None else _feat(residual)
+    check(_lib.lib().pcgc_conv_k3_fwd(_p(feats), feats.stride(0), _p(nbr), n, _p(weight), _p(bias), cin, cout,
+                                      _p(residual), 0 if residual is None else residual.stride(0), _p(out), out.stride(0),
+                                      EPI_RELU if relu else 0, _stream()), "pcgc_conv_k3_fwd")
+    return out
+
+
+def conv_k1(feats, weight, bias=None, residual=None, relu=False, out=None):
+    feats = _feat(feats)
+    n, cin = feats.shape
+    assert weight.dim() == 2 and weight.shape[0] == cin and weight.is_contiguous()
+    cout = weight.shape[1]
+    out = _out_slice(out, n, cout, feats.device)
+    residual = None if residual is None else _feat(residual)
+    check(_lib.lib().pcgc_conv_k1_fwd(_p(feats), feats.stride(0), n, _p(weight), _p(bias), cin, cout, _p(residual),
+                                      0 if residual is None else residual.stride(0), _p(out), out.stride(0),
+                                      EPI_RELU if relu else 0, _stream()), "pcgc_conv_k1_fwd")
+    return out
+
+
+def conv_k2s2(feats, in_keys, child_rows, child_off, weight, bias=None, relu=False, out=None):
+    feats = _feat(feats)
+    cin = feats.shape[1]
+    n_par = child_off.shape[0] - 1
+    cout = weight.shape[2]
+    assert weight.shape[0] == 8 and weight.shape[1] == cin and weight.is_contiguous()
+    out = _out_slice(out, n_par, cout, feats.device)
+    check(_lib.lib().pcgc_conv_k2s2_fwd(_p(feats), feats.stride(0), _p(in_keys), _p(child_rows), _p(child_off), n_par,
+                                        _p(weight), _p(bias), cin, cout, _p(out), out.stride(0),
+                                        EPI_RELU if relu else 0, _stream()), "pcgc_conv_k2s2_fwd")
+    return out
+
+
+def convT_k2s2(feats, weight, bias=None, relu=False, out=None):
+    feats = _feat(feats)
+    n, cin = feats.shape
+    cout = weight.shape[2]
+    assert weight.shape[0] == 8 and weight.shape[1] == cin and weight.is_contiguous()
+    out = _out_slice(out, 8 * n, cout, feats.device)
+    check(_lib.lib().pcgc_convT_k2s2_fwd(_p(feats), feats.stride(0), n, _p(weight), _p(bias), cin, cout, _p(out),
+                                         out.stride(0), EPI_RELU if relu else 0, _stream()), "pcgc_convT_k2s2_fwd")
+    return out
+
+
+# ------------------------------------------------------------------ selection / pruning
+
+def topk_mask(logits: torch.Tensor, k: int) -> torch.Tensor:
+    """bool [n]: True on the k largest entries of logits ([n] or [n,1] / strided column)."""
+    _need_cuda(logits)
+    if logits.dim() == 2:
+        assert logits.shape[1] == 1
+        ld = logits.stride(0)
+    else:
+        ld = logits.stride(0) if logits.numel() > 1 else 1
+    n = logits.shape[0]
+    L = _lib.lib()
+    mask = torch.empty(n, dtype=torch.uint8, device=logits.device)
+    nbytes = L.pcgc_topk_mask_ws_bytes(n)
+    ws = _ws(nbytes, logits.device)
+    check(L.pcgc_topk_mask(_p(logits), max(int(ld), 1), n, int(k), _p(mask), _p(ws), nbytes, _stream()), "pcgc_topk_mask")
+    return mask.bool()
+
+
+def prune(mask: torch.Tensor, keys, feats):
+    """stable compaction -> (keys_kept, feats_kept); one sync for the count."""
+    feats = _feat(feats)
+    n, c = feats.shape
+    L = _lib.lib()
+    dev = feats.device
+    m8 = mask.to(torch.uint8) if mask.dtype != torch.uint8 else mask
+    m8 = m8.contiguous()
+    keys_out = torch.empty(n, dtype=torch.int64, device=dev) if keys is not None else None
+    feats_out = torch.empty((n, c), dtype=torch.float32, device=dev)
+    n_kept = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = L.pcgc_prune_ws_bytes(n)
+    ws = _ws(nbytes, dev)
+    check(L.pcgc_prune(_p(m8), n, _p(keys), _p(feats), feats.stride(0), c, _p(keys_out), _p(feats_out), c, _p(n_kept),
+                       _p(ws), nbytes, _stream()), "pcgc_prune")
+    k = int(n_kept.item())
+    return (None if keys is None else keys_out[:k]), feats_out[:k]
+
+
+# ------------------------------------------------------------------ entropy bottleneck
+
+def pack_eb_params(matrices, biases, factors, device) -> torch.Tensor:
+    """12 reference tensors -> float32 [C, 48] block (layout in pcgc.h)."""
+    c = matrices[0].shape[0]
+    cols = [matrices[0].reshape(c, 3), matrices[1].reshape(c, 9), matrices[2].reshape(c, 9), matrices[3].reshape(c, 3),
+            biases[0].reshape(c, 3), biases[1].reshape(c, 3), biases[2].reshape(c, 3), biases[3].reshape(c, 1),
+            factors[0].reshape(c, 3), factors[1].reshape(c, 3), factors[2].reshape(c, 3), factors[3].reshape(c, 1)]
+    packed = torch.cat([t.detach().float().to(device) for t in cols] +
+                       [torch.zeros((c, EB_PPC - 44), dtype=torch.float32, device=device)], dim=1)
+    return packed.contiguous()
+
+
+def eb_likelihood(values: torch.Tensor, params: torch.Tensor) -> torch.Tensor:
+    values = _feat(values).contiguous()
+    n, c = values.shape
+    out = torch.empty_like(values)
+    check(_lib.lib().pcgc_eb_likelihood_fwd(_p(values), n, c, _p(params), _p(out), _stream()), "pcgc_eb_likelihood_fwd")
+    return out
+
+
+def eb_cdf_table(params: torch.Tensor, min_v: int, max_v: int):
+    """-> (cdf_float [C, L+1] float32, cdf_u16 [C, L+1] int16-bits) on the device."""
+    c = params.shape[0]
+    lp = int(max_v) - int(min_v) + 2
+    cdf = torch.empty((c, lp), dtype=torch.float32, device=params.device)
+    u16 = torch.empty((c, lp), dtype=torch.int16, device=params.device)
+    check(_lib.lib().pcgc_eb_cdf_table(_p(params), c, int(min_v), int(max_v), _p(cdf), _p(u16), _stream()),
+          "pcgc_eb_cdf_table")
+    return cdf, u16
+
+
+def eb_quantize(feats: torch.Tensor):
+    """round -> (symbols int16 [N,C] on device, min, max); one sync for min/max."""
+    feats = _feat(feats).contiguous()
+    count = feats.numel()
+    mm = torch.tensor([2 ** 31 - 1, -2 ** 31], dtype=torch.int32, device=feats.device)
+    L = _lib.lib()
+    check(L.pcgc_eb_round_minmax(_p(feats), count, _p(mm), _stream()), "pcgc_eb_round_minmax")
+    sym = torch.empty(feats.shape, dtype=torch.int16, device=feats.device)
+    check(L.pcgc_eb_symbols(_p(feats), count, _p(mm), _p(sym), _stream()), "pcgc_eb_symbols")
+    lo, hi = mm.tolist()
+    return sym, lo, hi
+
+
+# ------------------------------------------------------------------ range coder (host)
+
+def rc_encode_float(cdf_float: np.ndarray, sym: np.ndarray) -> bytes:
+    """cdf_float float32 [T, Lp] (symbol i uses row i % T), sym int16 [n]."""
+    cdf_float = np.ascontiguousarray(cdf_float, dtype=np.float32)
+    sym = np.ascontiguousarray(sym, dtype=np.int16).reshape(-1)
+    T, lp = cdf_float.shape
+    cap = 4 * sym.size + 64
+    out = np.empty(cap, dtype=np.uint8)
+    n = _lib.lib().pcgc_rc_encode_host(cdf_float.ctypes.data, T, lp, sym.ctypes.data, sym.size, out.ctypes.data, cap)
+    check(n, "pcgc_rc_encode_host")
+    if n > cap:
+        out = np.empty(n, dtype=np.uint8)
+        check(_lib.lib().pcgc_rc_encode_host(cdf_float.ctypes.data, T, lp, sym.ctypes.data, sym.size, out.ctypes.data, n))
+    return out[:n].tobytes()
+
+
+def rc_decode_float(cdf_float: np.ndarray, data: bytes, n_sym: int) -> np.ndarray:
+    cdf_float = np.ascontiguousarray(cdf_float, dtype=np.float32)
+    T, lp = cdf_float.shape
+    buf = np.frombuffer(data, dtype=np.uint8)
+    out = np.empty(n_sym, dtype=np.int16)
+    check(_lib.lib().pcgc_rc_decode_host(cdf_float.ctypes.data, T, lp, buf.ctypes.data if buf.size else None, buf.size,
+                                         out.ctypes.data, n_sym), "pcgc_rc_decode_host")
+    return out
+
+
+def rc_encode_u16(table: np.ndarray, sym: np.ndarray) -> bytes:
+    table = np.ascontiguousarray(table).view(np.uint16)
+    sym = np.ascontiguousarray(sym, dtype=np.int16).reshape(-1)
+    T, lp = table.shape
+    cap = 4 * sym.size + 64
+    out = np.empty(cap, dtype=np.uint8)
+    n = _lib.lib().pcgc_rc_encode_u16_host(table.ctypes.data, T, lp, sym.ctypes.data, sym.size, out.ctypes.data, cap)
+    check(n, "pcgc_rc_encode_u16_host")
+    if n > cap:
+        out = np.empty(n, dtype=np.uint8)
+        check(_lib.lib().pcgc_rc_encode_u16_host(table.ctypes.data, T, lp, sym.ctypes.data, sym.size, out.ctypes.data, n))
+    return out[:n].tobytes()
+
+
+def rc_decode_u16(table: np.ndarray, data: bytes, n_sym: int) -> np.ndarray:
+    table = np.ascontiguousarray(table).view(np.uint16)
+    T, lp = table.shape
+    buf = np.frombuffer(data, dtype=np.uint8)
+    out = np.empty(n_sym, dtype=np.int16)
+    check(_lib.lib().pcgc_rc_decode_u16_host(table.ctypes.data, T, lp, buf.ctypes.data if buf.size else None, buf.size,
+                                             out.ctypes.data, n_sym), "pcgc_rc_decode_u16_host")
+    return out

@@ -1,0 +1,79 @@
+"""The C-ABI library loads and exports every symbol include/pcgc.h declares; the HOST range
+coder (no GPU needed) is byte-identical to the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import rangecoder_ref as rc
+from pcgcv2_b200 import _lib, ops
+from test_oracle import _random_stream
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pcgc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcgc_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 30
+    handle = _lib.lib()
+    for n in names:
+        assert hasattr(handle, n), f"libpcgc.so lacks {n}"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes binding and pcgc.h diverge"
+    assert handle.pcgc_version() >= 100
+
+
+def test_error_reporting_without_gpu():
+    L = _lib.lib()
+    rc_ = L.pcgc_rc_encode_host(None, 0, 0, None, 0, None, 0)
+    assert rc_ < 0 and b"bad arguments" in L.pcgc_last_error()
+    with pytest.raises(_lib.PcgcError):
+        _lib.check(rc_, "x")
+
+
+@pytest.mark.parametrize("n,C,L", [(1, 1, 1), (1, 8, 5), (300, 8, 5), (257, 3, 19), (64, 8, 1), (5000, 8, 78),
+                                   (110272 // 8, 8, 5)])
+def test_host_rangecoder_matches_oracle_bytes(n, C, L):
+    cdf, sym, _ = _random_stream(n + L, n, C, L)
+    ref = rc.encode_float_cdf(np.broadcast_to(cdf, (n, C, L + 1)).copy(), sym)
+    got = ops.rc_encode_float(cdf, sym)
+    assert got == ref
+    assert (ops.rc_decode_float(cdf, got, n * C).reshape(n, C) == sym).all()
+    table = rc.cdf_float_to_u16(cdf)
+    assert ops.rc_encode_u16(table, sym) == ref
+    assert (ops.rc_decode_u16(table, ref, n * C).reshape(n, C) == sym).all()
+
+
+def test_host_rangecoder_per_symbol_tables_and_bounds():
+    cdf, sym, _ = _random_stream(9, 50, 4, 6)
+    per = np.broadcast_to(cdf, (50, 4, 7)).copy()
+    per[::3] = np.linspace(0, 1, 7, dtype=np.float32)
+    ref = rc.encode_float_cdf(per, sym)
+    got = ops.rc_encode_float(per.reshape(-1, 7), sym)
+    assert got == ref
+    assert (ops.rc_decode_float(per.reshape(-1, 7), got, 200).reshape(50, 4) == sym).all()
+    with pytest.raises(_lib.PcgcError):
+        ops.rc_encode_float(cdf, sym + 6)
+    # truncated / empty input decodes without reading out of bounds
+    assert ops.rc_decode_float(cdf, b"", 8).shape == (8,)
+
+
+def test_morton_key_layout():
+    """pack/unpack need a GPU; the key layout itself is pinned here with plain integers."""
+    def spread(v):
+        out = 0
+        for i in range(19):
+            out |= ((v >> i) & 1) << (3 * i)
+        return out
+    x, y, z, b = 0x5A5A5 & 0x7FFFF, 0x12345, 0x7FFFF, 5
+    key = (b << 57) | spread(x) | (spread(y) << 1) | (spread(z) << 2)
+    parent = (b << 57) | spread(x >> 1) | (spread(y >> 1) << 1) | (spread(z >> 1) << 2)
+    mask = (1 << 57) - 1
+    assert (key & ~mask) | ((key & mask) >> 3) == parent
+    assert key & 7 == (x & 1) + 2 * (y & 1) + 4 * (z & 1)

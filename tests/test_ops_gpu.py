@@ -1,0 +1,307 @@
+"""Parity of every CUDA operator (through the C ABI) against the CPU oracle, on seeded inputs.
+
+Integer / index work is compared bit-exactly; float32 convolutions within
+max|d| <= 2e-5 * max|ref| per layer (the north star allows 1e-4; different but valid
+summation orders of the same fp32 products give ~1e-6)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import entropy_ref, rangecoder_ref, sparse_ref as S
+from pcgcv2_b200 import ops, synth
+from util import GOLDEN, canon, load_ckpt, with_batch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+CONV_TOL = 2e-5
+
+
+def _cloud(seed, n=4000, size=40, batch=1, stride=1):
+    rng = np.random.default_rng(seed)
+    pts = np.unique(rng.integers(0, size, size=(n, 3)), axis=0)
+    rng.shuffle(pts)                                        # arbitrary (user) row order
+    c = with_batch(pts * stride)
+    if batch > 1:
+        c[:, 0] = rng.integers(0, batch, size=len(c))
+    return c
+
+
+def _surface(seed=0):
+    pts = synth.ellipsoid_vox8(seed, n=200_000)             # ~50 k voxels, surface-like
+    return with_batch(pts)
+
+
+def _keys(coords, stride=1):
+    return ops.pack_keys(torch.from_numpy(coords).to(DEV), stride)
+
+
+def _rel_err(got, ref):
+    ref = ref.float()
+    return float((got.cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------ coordinates
+
+@pytest.mark.parametrize("stride", [1, 2, 8])
+def test_pack_unpack_roundtrip(stride):
+    c = _cloud(1, batch=3, stride=stride)
+    c[0, 1:] = 0
+    c[1, 1:] = ((1 << 19) - 1) * stride if stride == 1 else c[1, 1:]
+    keys = _keys(c, stride)
+    assert (ops.unpack_keys(keys, stride).cpu().numpy() == c).all()
+    assert keys.unique().numel() == len(np.unique(c, axis=0))
+
+
+def test_pack_rejects_bad_coordinates():
+    for bad in ([[0, -1, 0, 0]], [[0, 1 << 19, 0, 0]], [[127, 0, 0, 0]]):
+        with pytest.raises(ValueError):
+            ops.pack_keys(torch.tensor(bad, dtype=torch.int32, device=DEV), 1)
+    with pytest.raises(ValueError):
+        ops.pack_keys(torch.tensor([[0, 3, 0, 0]], dtype=torch.int32, device=DEV), 2)     # not a multiple
+    assert ops.pack_keys(torch.zeros((0, 4), dtype=torch.int32, device=DEV), 1).numel() == 0
+
+
+def test_hash_dedup_first_seen():
+    c = _cloud(2, n=3000, size=12)
+    dup = np.concatenate([c, c[::5], c[::7]])
+    keys = _keys(dup)
+    table = ops.HashTable(keys)
+    assert table.n_dup == len(dup) - len(c)
+    keep = table.keep_flags(keys).cpu().numpy().astype(bool)
+    _, first = S.unique_coords(dup)
+    assert (np.nonzero(keep)[0] == first).all()
+    assert ops.HashTable(_keys(c)).n_dup == 0
+
+
+def test_isin_matches_oracle():
+    a, b = _cloud(3, batch=2), _cloud(4, batch=2)
+    found = ops.HashTable(_keys(b)).contains(_keys(a)).cpu().numpy()
+    assert (found == S.isin(a, b)).all()
+    assert found.any() and not found.all()
+
+
+@pytest.mark.parametrize("stride,batch", [(1, 1), (4, 2)])
+def test_kernel_map_k3_bit_exact(stride, batch):
+    c = _cloud(5, n=6000, size=24, batch=batch, stride=stride)
+    keys = _keys(c, stride)
+    nbr, npairs = ops.kernel_map_k3(keys, ops.HashTable(keys), count_pairs=True)
+    ref = S.kernel_map_k3(c, stride)
+    assert (nbr.cpu().numpy().T == ref).all()
+    assert int(npairs.item()) == int((ref >= 0).sum())
+
+
+def test_kernel_map_grid_edges():
+    """voxels on the 0 / max faces: neighbours outside the key range are reported missing."""
+    m = (1 << 19) - 1
+    c = with_batch([[0, 0, 0], [1, 0, 0], [m, m, m], [m - 1, m, m], [0, m, 0]])
+    keys = _keys(c)
+    nbr = ops.kernel_map_k3(keys, ops.HashTable(keys)).cpu().numpy().T
+    assert (nbr == S.kernel_map_k3(c, 1)).all()
+
+
+def test_kernel_map_surface_cloud():
+    c = _surface()
+    keys = _keys(c)
+    nbr = ops.kernel_map_k3(keys, ops.HashTable(keys)).cpu().numpy().T
+    assert (nbr == S.kernel_map_k3(c, 1)).all()
+
+
+@pytest.mark.parametrize("presorted", [False, True])
+def test_stride_down_map(presorted):
+    c = _cloud(6, n=5000, size=30, batch=2, stride=2)
+    keys = _keys(c, 2)
+    if presorted:
+        keys, order = ops.argsort_u64(keys)
+        c = c[order.cpu().numpy()]
+    pk, rows, off = ops.stride_down(keys, keys_are_sorted=presorted)
+    out_ref, parent_ref, kidx_ref = S.stride_down(c, 2)
+    pc = ops.unpack_keys(pk, 4).cpu().numpy()
+    assert (canon(pc) == canon(out_ref)).all()
+    rows, off = rows.cpu().numpy(), off.cpu().numpy()
+    assert off[0] == 0 and off[-1] == len(c) and sorted(rows.tolist()) == list(range(len(c)))
+    for p in range(len(pc)):                                  # every child sits under its own parent
+        kids = rows[off[p]:off[p + 1]]
+        assert 1 <= len(kids) <= 8
+        assert (out_ref[parent_ref[kids]] == pc[p]).all()
+    assert ((keys.cpu().numpy() & 7) == kidx_ref).all()
+
+
+def test_upsample_keys():
+    c = _cloud(7, n=500, size=10, batch=2, stride=4)
+    child = ops.unpack_keys(ops.upsample_keys(_keys(c, 4)), 2).cpu().numpy()
+    _, ref = S.convT_k2s2(torch.zeros(len(c), 1), c, 4, torch.zeros(8, 1, 1), None)
+    assert (child == ref).all()
+
+
+def test_argsort_canonical_order():
+    """sort_spare_tensor order (data_utils.py:91-101) from the device argsort."""
+    c = _cloud(8, n=3000, size=33, stride=8)
+    ct = torch.from_numpy(c).to(DEV).long()
+    step = int(c.max()) + 1
+    key = ct[:, 0] + ct[:, 1] * step + ct[:, 2] * step ** 2 + ct[:, 3] * step ** 3
+    _, order = ops.argsort_u64(key)
+    assert (order.cpu().numpy() == np.argsort(S.sort_key(c), kind="stable")).all()
+
+
+# ------------------------------------------------------------------ convolutions
+
+MODEL_K3 = [(1, 16), (32, 8), (8, 16), (8, 8), (32, 32), (64, 16), (16, 32), (16, 16), (64, 64), (64, 1), (32, 1),
+            (16, 4), (4, 8), (4, 4), (16, 1)]
+
+
+@pytest.mark.parametrize("cin,cout", MODEL_K3 + [(64, 32), (32, 64), (128, 128), (3, 5), (12, 20), (128, 8)])
+def test_conv_k3_vs_oracle(cin, cout):
+    c = _cloud(cin * 131 + cout, n=3000, size=16)
+    keys = _keys(c)
+    nbr = ops.kernel_map_k3(keys, ops.HashTable(keys))
+    g = torch.Generator().manual_seed(cin + 7 * cout)
+    f = torch.randn(len(c), cin, generator=g)
+    w = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    b = torch.randn(1, cout, generator=g)
+    ref = S.conv_k3(f, c, 1, w, b)
+    got = ops.conv_k3(f.to(DEV), nbr, w.to(DEV), b.to(DEV))
+    assert _rel_err(got, ref) < CONV_TOL
+    # fused epilogue: residual + ReLU, written into a column slice of a wider tensor (ME.cat fusion)
+    if cout % 4 == 0:
+        res = torch.randn(len(c), cout, generator=g)
+        wide = torch.full((len(c), cout + 8), -7.0, device=DEV)
+        ops.conv_k3(f.to(DEV), nbr, w.to(DEV), b.to(DEV), residual=res.to(DEV), relu=True, out=wide[:, 4:4 + cout])
+        assert _rel_err(wide[:, 4:4 + cout], torch.relu(ref + res)) < CONV_TOL
+        assert (wide[:, :4] == -7).all() and (wide[:, 4 + cout:] == -7).all()
+
+
+def test_conv_k3_surface_and_ragged_sizes():
+    c = _surface()
+    keys = _keys(c)
+    nbr = ops.kernel_map_k3(keys, ops.HashTable(keys))
+    g = torch.Generator().manual_seed(0)
+    for n in (len(c), 1, 63, 65, 2049):                       # tile tails of both kernel families
+        cc = c[:n]
+        kk = _keys(cc)
+        nb = ops.kernel_map_k3(kk, ops.HashTable(kk)) if n != len(c) else nbr
+        for cin, cout in ((16, 16), (64, 64)):
+            f = torch.randn(n, cin, generator=g)
+            w = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+            ref = S.conv_k3(f, cc, 1, w, None)
+            got = ops.conv_k3(f.to(DEV), nb, w.to(DEV))
+            assert _rel_err(got, ref) < CONV_TOL
+
+
+def test_conv_empty_input():
+    f = torch.zeros((0, 16), device=DEV)
+    nbr = torch.zeros((27, 0), dtype=torch.int32, device=DEV)
+    assert ops.conv_k3(f, nbr, torch.zeros(27, 16, 16, device=DEV)).shape == (0, 16)
+    assert ops.conv_k1(f, torch.zeros(16, 8, device=DEV)).shape == (0, 8)
+    assert ops.convT_k2s2(f, torch.zeros(8, 16, 8, device=DEV)).shape == (0, 8)
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 8), (8, 16), (64, 16), (16, 32), (16, 4), (4, 8), (128, 64), (5, 3)])
+def test_conv_k1_vs_oracle(cin, cout):
+    g = torch.Generator().manual_seed(cin * cout)
+    f = torch.randn(2111, cin, generator=g)
+    w = torch.randn(cin, cout, generator=g) / np.sqrt(cin)
+    b = torch.randn(1, cout, generator=g)
+    got = ops.conv_k1(f.to(DEV), w.to(DEV), b.to(DEV), relu=True)
+    assert _rel_err(got, torch.relu(S.conv_k1(f, w, b))) < CONV_TOL
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 32), (32, 64), (64, 32), (8, 8), (6, 10)])
+def test_conv_k2s2_vs_oracle(cin, cout):
+    c = _cloud(cin + cout, n=5000, size=26, batch=2)
+    keys = _keys(c)
+    pk, rows, off = ops.stride_down(keys)
+    g = torch.Generator().manual_seed(cin)
+    f = torch.randn(len(c), cin, generator=g)
+    w = torch.randn(8, cin, cout, generator=g) / np.sqrt(8 * cin)
+    b = torch.randn(1, cout, generator=g)
+    ref, ref_c = S.conv_k2s2(f, c, 1, w, b)
+    got = ops.conv_k2s2(f.to(DEV), keys, rows, off, w.to(DEV), b.to(DEV))
+    got_c = ops.unpack_keys(pk, 2).cpu().numpy()
+    lut = {tuple(r): i for i, r in enumerate(ref_c.tolist())}
+    perm = torch.tensor([lut[tuple(r)] for r in got_c.tolist()])
+    assert _rel_err(got, ref[perm]) < CONV_TOL
+
+
+@pytest.mark.parametrize("cin,cout", [(8, 64), (64, 32), (32, 16), (16, 8), (6, 10)])
+def test_convT_k2s2_vs_oracle(cin, cout):
+    c = _cloud(cin * 3 + cout, n=1500, size=14, stride=2)
+    g = torch.Generator().manual_seed(cout)
+    f = torch.randn(len(c), cin, generator=g)
+    w = torch.randn(8, cin, cout, generator=g) / np.sqrt(cin)
+    b = torch.randn(1, cout, generator=g)
+    ref, ref_c = S.convT_k2s2(f, c, 2, w, b)
+    got = ops.convT_k2s2(f.to(DEV), w.to(DEV), b.to(DEV), relu=True)
+    assert _rel_err(got, torch.relu(ref)) < CONV_TOL
+    assert (ops.unpack_keys(ops.upsample_keys(_keys(c, 2)), 1).cpu().numpy() == ref_c).all()
+
+
+# ------------------------------------------------------------------ selection / pruning
+
+@pytest.mark.parametrize("n,k", [(1, 1), (1000, 1), (1000, 999), (100_003, 37_111), (5, 0), (5, 9), (1_700_000, 800_000)])
+def test_topk_mask_matches_torch_topk(n, k):
+    g = torch.Generator().manual_seed(n + k)
+    x = torch.randn(n, 1, generator=g) * 5
+    mask = ops.topk_mask(x.to(DEV), k).cpu().numpy()
+    assert (mask == S.topk_mask(x, k)).all()
+
+
+def test_topk_mask_ties_and_specials():
+    x = torch.tensor([1.0, 2.0, 2.0, 2.0, -0.0, 0.0, -3.0, 2.0, float("inf"), -float("inf")])
+    for k in range(0, 11):
+        m = ops.topk_mask(x.to(DEV), k).cpu().numpy()
+        assert m.sum() == min(k, 10)
+        kept, dropped = x[torch.from_numpy(m)], x[torch.from_numpy(~m)]
+        if len(kept) and len(dropped):
+            assert kept.min() >= dropped.max()
+    m = ops.topk_mask(x.to(DEV), 3).cpu().numpy()              # ties at the threshold: lowest rows win
+    assert m.nonzero()[0].tolist() == [1, 2, 8]
+
+
+@pytest.mark.parametrize("channels", [1, 16, 64, 6])
+def test_prune_stable_compaction(channels):
+    c = _cloud(9, n=5000, size=30)
+    keys = _keys(c)
+    g = torch.Generator().manual_seed(channels)
+    f = torch.randn(len(c), channels, generator=g)
+    mask = torch.rand(len(c), generator=g) < 0.4
+    k_out, f_out = ops.prune(mask.to(DEV), keys, f.to(DEV))
+    f_ref, c_ref = S.prune(f, c, mask.numpy())
+    assert (ops.unpack_keys(k_out, 1).cpu().numpy() == c_ref).all()
+    assert torch.equal(f_out.cpu(), f_ref)
+    for m in (torch.zeros(len(c), dtype=torch.bool), torch.ones(len(c), dtype=torch.bool)):
+        k2, f2 = ops.prune(m.to(DEV), keys, f.to(DEV))
+        assert len(k2) == int(m.sum()) == len(f2)
+
+
+# ------------------------------------------------------------------ entropy bottleneck
+
+@pytest.mark.parametrize("name", ["r3", "r7"])
+def test_eb_likelihood_and_tables_vs_reference_golden(name):
+    gold = np.load(os.path.join(GOLDEN, f"entropy_{name}.npz"))
+    sd = load_ckpt(name)
+    p = entropy_ref.params_from_state_dict(sd)
+    params = ops.pack_eb_params(p["matrices"], p["biases"], p["factors"], DEV)
+    lik = ops.eb_likelihood(torch.from_numpy(gold["values"]).to(DEV), params).cpu().numpy()
+    np.testing.assert_allclose(lik, gold["likelihood"], rtol=2e-5, atol=1e-9)
+    for key in gold.files:
+        if not key.startswith("cdf_"):
+            continue
+        _, lo, hi = key.split("_")
+        cdf, u16 = ops.eb_cdf_table(params, int(lo), int(hi))
+        np.testing.assert_allclose(cdf.cpu().numpy(), gold[key], rtol=0, atol=2e-6)
+        ref_u16 = rangecoder_ref.cdf_float_to_u16(gold[key]).astype(np.int64)
+        got_u16 = u16.cpu().numpy().view(np.uint16).astype(np.int64)
+        assert np.abs(got_u16[:, :-1] - ref_u16[:, :-1]).max() <= 1           # integer table within 1 count
+        assert (np.diff(got_u16[:, :-1], axis=1) > 0).all()                   # strictly increasing rows
+
+
+def test_eb_quantize_symbols():
+    g = torch.Generator().manual_seed(3)
+    f = torch.randn(1521, 8, generator=g) * 3
+    f[0, 0], f[1, 1], f[2, 2] = 0.5, 1.5, -2.5                               # half-to-even cases
+    sym, lo, hi = ops.eb_quantize(f.to(DEV))
+    ref_sym, ref_lo, ref_hi = entropy_ref.quantize_symbols(f)
+    assert (lo, hi) == (int(ref_lo), int(ref_hi))
+    assert torch.equal(sym.cpu(), ref_sym)
