@@ -41,6 +41,7 @@ def _conv(sd, name, feats, coords, stride, maps, record=None):
         out = S.conv_from_map(feats, maps.k3(coords, stride), w, b)
     if record is not None:
         record[name] = out
+        record[name + ".C"] = coords
     return out
 
 
@@ -55,6 +56,7 @@ def _irn(sd, prefix, x, coords, stride, maps, record=None):
     out = torch.cat([out0, out1], dim=1) + x
     if record is not None:
         record[prefix] = out
+        record[prefix + ".C"] = coords
     return out
 
 

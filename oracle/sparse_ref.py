@@ -56,12 +56,14 @@ class _Lookup:
             assert (np.diff(self.sorted) > 0).all(), "coordinate map holds duplicates"
 
     def find(self, coords: np.ndarray) -> np.ndarray:
-        key = coord_key(coords)
+        c = np.asarray(coords, dtype=np.int64)
+        inside = ((c[:, 1:] >= -_OFF) & (c[:, 1:] < _OFF)).all(axis=1)   # queries outside the key range miss
+        key = coord_key(np.where(inside[:, None], c, 0))
         if len(self.sorted) == 0:
             return np.full(len(key), -1, dtype=np.int64)
         pos = np.searchsorted(self.sorted, key)
         pos_c = np.minimum(pos, len(self.sorted) - 1)
-        hit = self.sorted[pos_c] == key
+        hit = (self.sorted[pos_c] == key) & inside
         return np.where(hit, self.order[pos_c], -1).astype(np.int64)
 
 

@@ -83,9 +83,10 @@ __host__ __device__ __forceinline__ uint64_t make_key(uint32_t b, uint32_t x, ui
 __host__ __device__ __forceinline__ void split_key(uint64_t key, uint32_t &b, uint32_t &x, uint32_t &y,
                                                    uint32_t &z) {
     b = (uint32_t)(key >> 57);
-    x = compact3(key);
-    y = compact3(key >> 1);
-    z = compact3(key >> 2);
+    const uint64_t m = key & kMortonMask;       // the batch bits must not leak into the de-interleave
+    x = compact3(m);
+    y = compact3(m >> 1);
+    z = compact3(m >> 2);
 }
 
 // one level up / down the octree: the batch bits stay in place, only the Morton field shifts

@@ -1,0 +1,173 @@
+"""End-to-end parity of the CUDA codec (pcgcv2_b200.Codec and the MinkowskiEngine shim) against
+the CPU oracle with the reference's shipped weights (r3 / r7 fixtures).
+
+Bars (BASELINE.json north_star): occupancy coordinates bit-exact after canonical sort, activations
+within 1e-4 relative (max|d| / max|ref| per layer), bits within 1e-4 relative, D1 PSNR within 0.01 dB."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import codec_ref, metrics_ref, sparse_ref as S
+from pcgcv2_b200 import ops, synth
+from pcgcv2_b200.codec import Codec
+from util import GOLDEN, canon, load_ckpt, with_batch
+
+pytestmark = pytest.mark.gpu
+ACT_TOL = 1e-4
+
+
+def _sorted_rows(feats, coords):
+    order = np.lexsort(np.asarray(coords).T[::-1])
+    return feats[torch.from_numpy(order)], np.asarray(coords)[order]
+
+
+def _check_layers(codec_record, oracle_record, relu_names=()):
+    checked = 0
+    for name, (t, keys, stride) in codec_record.items():
+        if name not in oracle_record or keys is None:
+            continue
+        ref = oracle_record[name]
+        if any(name.startswith(p) for p in relu_names):
+            ref = torch.relu(ref)
+        ref, ref_c = _sorted_rows(ref, oracle_record[name + ".C"])
+        got, got_c = _sorted_rows(t.cpu(), ops.unpack_keys(keys, stride).cpu().numpy())
+        assert (got_c == ref_c).all(), f"{name}: coordinate sets differ"
+        err = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        assert err < ACT_TOL, f"{name}: relative error {err:.2e}"
+        checked += 1
+    return checked
+
+
+@pytest.fixture(scope="module")
+def r3():
+    torch.set_flush_denormal(True)
+    return load_ckpt("r3")
+
+
+def test_cube32_layers_bitstream_and_decode_match_oracle(r3):
+    """config 1: 32^3 random-occupancy cube, r3 checkpoint."""
+    coords = with_batch(synth.random_cube(0, 32, 0.1))
+    rec_ref = {}
+    st_ref = codec_ref.encode(r3, coords, rec_ref)
+    dec_ref, _ = codec_ref.decode(r3, st_ref, record=rec_ref)
+
+    codec = Codec(r3)
+    codec.record = {}
+    st = codec.encode(coords[:, 1:])
+    dec = codec.decode(st)
+    n = _check_layers(codec.record, rec_ref, relu_names=("encoder.down", "decoder.up", "encoder.conv0",
+                                                          "encoder.conv1", "encoder.conv2", "decoder.conv0",
+                                                          "decoder.conv1", "decoder.conv2"))
+    assert n >= 30
+    assert (st.coords == st_ref["C_coords"]).all()                       # canonical order, bit-exact
+    assert st.H == st_ref["H"] and st.num_points == st_ref["num_points"]
+    assert abs(len(st.F) - len(st_ref["F"])) * 8 <= max(8, 1e-4 * 8 * len(st_ref["F"]))
+    assert (canon(dec) == canon(dec_ref[:, 1:])).all()                   # decoded occupancy, bit-exact
+    gold = np.load(os.path.join(GOLDEN, "oracle_cube32_r3.npz"))
+    assert (canon(dec) == canon(gold["dec_C"][:, 1:])).all()
+
+
+@pytest.mark.parametrize("name", ["r3", "r7"])
+def test_vox8_known_answer(name):
+    """checkpoint-behaviour KAT: ellipsoid shell, 91 568 voxels."""
+    kat = json.load(open(os.path.join(GOLDEN, "oracle_vox8_kat.json")))
+    pts = synth.ellipsoid_vox8()
+    codec = Codec(load_ckpt(name))
+    st = codec.encode(pts)
+    dec = codec.decode(st)
+    assert len(st.coords) == kat[name]["N3"] and len(dec) == kat[name]["N_out"]
+    assert abs(len(st.F) - kat[name]["F_bytes"]) * 8 <= max(8, 1e-4 * 8 * kat[name]["F_bytes"])
+    assert abs(metrics_ref.d1_psnr(pts, dec, 256) - kat[name]["D1_psnr"]) < 0.01
+
+
+def test_empty_tiny_and_duplicate_inputs(r3):
+    codec = Codec(r3)
+    one = codec.decode(codec.encode(np.array([[5, 6, 7]], dtype=np.int32)))
+    assert one.shape == (1, 3)
+    pts = synth.random_cube(1, 16, 0.2)
+    dup = np.concatenate([pts, pts[::3]])
+    a, b = codec.encode(pts), codec.encode(dup)
+    assert a.F == b.F and (a.coords == b.coords).all() and a.num_points == b.num_points
+
+
+def test_rho_changes_output_size(r3):
+    pts = synth.random_cube(2, 32, 0.1)
+    codec = Codec(r3)
+    st = codec.encode(pts)
+    assert len(codec.decode(st, rho=1.0)) == len(pts)
+    assert len(codec.decode(st, rho=2.0)) == 2 * len(pts)
+
+
+def test_shim_model_matches_codec_and_oracle(r3):
+    """the same network driven through the drop-in MinkowskiEngine operator surface."""
+    from pcgcv2_b200.model import load_model
+    import MinkowskiEngine as ME
+    from data_utils import sort_spare_tensor
+    pts = synth.ellipsoid_vox8(n=150_000)
+    coords = with_batch(pts)
+    rng = np.random.default_rng(0)
+    coords = coords[rng.permutation(len(coords))]                        # user order is arbitrary
+    model = load_model(r3)
+    with torch.no_grad():
+        c, f = ME.utils.sparse_collate([torch.from_numpy(coords[:, 1:])], [torch.ones(len(coords), 1)])
+        x = ME.SparseTensor(features=f, coordinates=c, tensor_stride=1, device="cuda")
+        assert (x.C.cpu().numpy() == coords).all()                       # row order preserved (Appendix A.2)
+        y_list = model.encoder(x)
+        y = sort_spare_tensor(y_list[0])
+    st_ref = codec_ref.encode(r3, coords)
+    assert (y.C.cpu().numpy() == st_ref["y_C"]).all()
+    err = float((y.F.cpu() - st_ref["y_F"]).abs().max() / st_ref["y_F"].abs().max())
+    assert err < ACT_TOL
+    assert [len(t) for t in y_list] == [len(st_ref["y_C"])] + np.frombuffer(st_ref["num_points"], np.int32).tolist()[:2]
+    # decoder through the shim, fed with the oracle's quantised bottleneck
+    nums = np.frombuffer(st_ref["num_points"], np.int32).tolist()
+    yq = ME.SparseTensor(features=st_ref["y_F"].round().cuda(), coordinates=torch.from_numpy(st_ref["y_C"]).cuda(),
+                         tensor_stride=8, device="cuda")
+    with torch.no_grad():
+        _, out = model.decoder(yq, [[n] for n in nums], [None] * 3, training=False)
+    dec_ref, _ = codec_ref.decode(r3, st_ref)
+    assert (canon(out.C.cpu().numpy()) == canon(dec_ref)).all()
+
+
+def test_shim_error_behaviour(r3):
+    import pcgcv2_b200
+    pcgcv2_b200.install_shims()
+    import MinkowskiEngine as ME
+    f = torch.ones(4, 1)
+    c = torch.tensor([[0, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=torch.int32)
+    with pytest.raises(ValueError):
+        ME.SparseTensor(features=f, coordinates=c.long(), device="cuda")            # coords must be int32
+    with pytest.raises(ValueError):
+        ME.SparseTensor(features=f, coordinates=c, device="cpu")                    # no CPU backend
+    a = ME.SparseTensor(features=f, coordinates=c, device="cuda")
+    b = ME.SparseTensor(features=f, coordinates=c, device="cuda")
+    with pytest.raises(ValueError):
+        ME.cat(a, b)                                                                # different coordinate maps
+    with pytest.raises(ValueError):
+        a + b
+    d = ME.SparseTensor(features=torch.ones(6, 1), coordinates=torch.cat([c, c[:2]]), device="cuda")
+    assert len(d) == 4                                                              # duplicates collapse (A.2)
+
+
+@pytest.mark.slow
+def test_vox10_roundtrip_properties(r3):
+    """BASELINE config 2 size (synthetic vox10, 795 124 voxels): size-independent properties."""
+    pts = synth.synthetic_vox10(0)
+    assert len(pts) == 795124
+    codec = Codec(r3)
+    st = codec.encode(pts)
+    n2, n1, n0 = np.frombuffer(st.num_points, np.int32).tolist()
+    assert n0 == len(pts) and len(st.coords) < n2 < n1 < n0
+    # the bottleneck coordinates are exactly the occupied 8x8x8 cells of the input
+    cells = np.unique(pts // 8, axis=0)
+    assert (canon(st.coords) == canon(cells)).all()
+    dec = codec.decode(st)
+    assert len(dec) == n0 and len(np.unique(dec, axis=0)) == n0
+    assert (np.unique(dec // 8, axis=0) == canon(cells)).all()                      # decoded voxels stay inside coded cells
+    assert codec.decode(st).tolist() == dec.tolist()                                # deterministic
+    bpp = st.bits() / n0
+    assert 0.03 < bpp < 0.12                                                         # r3 operating point (~0.07 bpp features)
+    assert metrics_ref.d1_psnr(pts, dec, 1024) > 68.0
