@@ -70,6 +70,7 @@ class Codec:
         self.eb_params = ops.pack_eb_params(g("_matrices"), g("_biases"), g("_factors"), self.device)
         self.channels = self.eb_params.shape[0]
         self.record = None              # set to a dict to capture per-layer activations (parity tests)
+        self.probe = {}                 # layer name -> list of (start, end) CUDA event pairs (bench.py roofline)
 
     # ---------------------------------------------------------------- layers
     def _rec(self, name, t, level=None):
@@ -78,8 +79,16 @@ class Codec:
                                  None if level is None else level.stride)
 
     def _k3(self, name, x, level, relu=False, residual=None, out=None):
+        ev = self.probe.get(name)
+        if ev is not None:
+            nbr = level.nbr                                    # keep the (cached) map build outside the probe
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
         y = ops.conv_k3(x, level.nbr, self.w[name + ".kernel"], self.w[name + ".bias"], residual=residual, relu=relu,
                         out=out)
+        if ev is not None:
+            end.record()
+            ev.append((start, end))
         if out is None:
             self._rec(name, y, level)
         return y
@@ -173,8 +182,8 @@ class Codec:
                       coords=c3.cpu().numpy(), stats={"N": num_points, "sym_range": (lo, hi)})
 
     @torch.no_grad()
-    def decode(self, stream: Stream, rho: float = 1.0) -> np.ndarray:
-        """-> decoded voxel coordinates int32 [N_out, 3] (host)."""
+    def decode(self, stream: Stream, rho: float = 1.0, to_host: bool = True):
+        """-> decoded voxel coordinates int32 [N_out, 3] (host array, or device tensor if not to_host)."""
         shape = np.frombuffer(stream.H[:8], dtype=np.int32)
         lo = int(np.frombuffer(stream.H[9:13], dtype=np.float32)[0])
         hi = int(np.frombuffer(stream.H[13:17], dtype=np.float32)[0])
@@ -190,4 +199,5 @@ class Codec:
         nums = np.frombuffer(stream.num_points, dtype=np.int32).tolist()
         nums[-1] = int(rho * nums[-1])                                   # coder.py:107
         level0, _, _ = self.synthesis(y[order.long()].contiguous(), level3, nums)
-        return ops.unpack_keys(level0.keys, 1)[:, 1:].cpu().numpy()
+        out = ops.unpack_keys(level0.keys, 1)[:, 1:]
+        return out.cpu().numpy() if to_host else out
