@@ -167,7 +167,7 @@ class Codec:
         """coords: int32 [N,3] (or [N,4] with the batch column; batch 0 only) host array or tensor."""
         coords = torch.as_tensor(coords, dtype=torch.int32)
         if coords.shape[1] == 3:
-            coords = torch.cat([torch.zeros((len(coords), 1), dtype=torch.int32), coords], dim=1)
+            coords = torch.cat([torch.zeros((len(coords), 1), dtype=torch.int32, device=coords.device), coords], dim=1)
         level0 = self._sorted_input(coords.to(self.device, non_blocking=True))
         y, level3, num_points = self.analysis(level0)
         c3 = ops.unpack_keys(level3.keys, 1)[:, 1:]                       # stride-8 coordinates / 8
