@@ -89,12 +89,25 @@ int pcgc_kernel_map_k3(const uint64_t *keys, int64_t n, const uint64_t *table_ke
  * -- autoencoder.py:78,97,116.  Parents = unique(parent(key)) in ascending key order.
  * Outputs: parent_keys[<=n], n_parents (device int32), child_rows int32 [n] (input rows
  * grouped by parent, ascending child index), child_off int32 [n_parents+1] (CSR offsets
- * into child_rows; caller provides n+1 entries).  keys_are_sorted != 0 promises ascending
+ * into child_rows; caller provides n+1 entries), parent_of int32 [n] (may be NULL): parent
+ * row of every input row.  keys_are_sorted != 0 promises ascending
  * keys (the order every map derived by this library has) and skips the radix sort. */
 size_t pcgc_stride_down_ws_bytes(int64_t n);
 int pcgc_stride_down(const uint64_t *keys, int64_t n, int32_t keys_are_sorted, uint64_t *parent_keys,
-                     int32_t *n_parents, int32_t *child_rows, int32_t *child_off, void *ws,
-                     size_t ws_bytes, void *stream);
+                     int32_t *n_parents, int32_t *child_rows, int32_t *child_off, int32_t *parent_of,
+                     void *ws, size_t ws_bytes, void *stream);
+
+/* a4  kernel map of a SORTED child set derived from the kernel map of its parent set -- no
+ * hashing: neighbour (c + d) of child position c lies in parent neighbour floor((c+d)/2) at
+ * child position (c+d)&1.  parent_info[p] = (first child row << 8) | occupancy byte, from
+ * pcgc_parent_info; parent_of[i] from pcgc_stride_down.  parent_info == NULL selects the
+ * full-octet mode (child set = generative up-sampling output, row 8*p + c; no tables read).
+ * parent_nbr is the parent's map [27][n_parents]; nbr the child's [27][n]. */
+int pcgc_parent_info(const uint64_t *child_keys, const int32_t *child_off, int64_t n_parents,
+                     uint64_t *parent_info, void *stream);
+int pcgc_kernel_map_k3_from_parent(const uint64_t *child_keys, const int32_t *parent_of,
+                                   const uint64_t *parent_info, const int32_t *parent_nbr,
+                                   int64_t n_parents, int64_t n, int32_t *nbr, void *stream);
 
 /* a6  output coordinate map of ME.MinkowskiGenerativeConvolutionTranspose(k=2, s=2)
  * -- autoencoder.py:155,182,209: child_keys[8*i + k] = child(keys[i], k) (Morton field << 3 | k). */
@@ -139,11 +152,13 @@ size_t pcgc_topk_mask_ws_bytes(int64_t n);
 int pcgc_topk_mask(const float *logits, int32_t ld, int64_t n, int64_t k, uint8_t *mask, void *ws,
                    size_t ws_bytes, void *stream);
 /* a8  ME.MinkowskiPruning()(x, mask) -- autoencoder.py:237,247: stable compaction of keys and
- * feature rows; n_kept (device int32) receives the count. */
+ * feature rows; n_kept (device int32) receives the count.  If nbr_in ([27][n], the k=3 kernel
+ * map of the unpruned set) and nbr_out are given, the kernel map of the pruned set is produced
+ * too, as [27][n_kept] (compact, caller provides 27*n entries): no re-hashing after pruning. */
 size_t pcgc_prune_ws_bytes(int64_t n);
 int pcgc_prune(const uint8_t *mask, int64_t n, const uint64_t *keys, const float *feats, int32_t ld,
                int32_t channels, uint64_t *keys_out, float *feats_out, int32_t out_ld, int32_t *n_kept,
-               void *ws, size_t ws_bytes, void *stream);
+               const int32_t *nbr_in, int32_t *nbr_out, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- entropy bottleneck (rows a12, a13, a14) ---------------------------------------------
  * params: the 12 reference tensors entropy_bottleneck._matrices.0..3, _biases.0..3,

@@ -41,7 +41,9 @@ SIGNATURES = {
     "pcgc_hash_contains": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p]),
     "pcgc_kernel_map_k3": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_p]),
     "pcgc_stride_down_ws_bytes": (c_sz, [c_i64]),
-    "pcgc_stride_down": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "pcgc_stride_down": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "pcgc_parent_info": (ctypes.c_int, [c_p, c_p, c_i64, c_p, c_p]),
+    "pcgc_kernel_map_k3_from_parent": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "pcgc_upsample_keys": (ctypes.c_int, [c_p, c_i64, c_p, c_p]),
     "pcgc_argsort_ws_bytes": (c_sz, [c_i64]),
     "pcgc_argsort_u64": (ctypes.c_int, [c_p, c_i64, ctypes.c_int, c_p, c_p, c_p, c_sz, c_p]),
@@ -52,7 +54,7 @@ SIGNATURES = {
     "pcgc_topk_mask_ws_bytes": (c_sz, [c_i64]),
     "pcgc_topk_mask": (ctypes.c_int, [c_p, c_i32, c_i64, c_i64, c_p, c_p, c_sz, c_p]),
     "pcgc_prune_ws_bytes": (c_sz, [c_i64]),
-    "pcgc_prune": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_p, c_i32, c_p, c_p, c_sz, c_p]),
+    "pcgc_prune": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "pcgc_eb_likelihood_fwd": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p]),
     "pcgc_eb_cdf_table": (ctypes.c_int, [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p]),
     "pcgc_eb_round_minmax": (ctypes.c_int, [c_p, c_i64, c_p, c_p]),

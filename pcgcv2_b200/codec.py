@@ -37,25 +37,28 @@ class Stream:
 
 
 class _Level:
-    """one coordinate set (sorted Morton keys) with its lazily built hash table and k3 kernel map."""
+    """one coordinate set (sorted Morton keys) with its lazily built k3 kernel map.
 
-    def __init__(self, keys: torch.Tensor, stride: int):
+    Maps are hierarchical: a set that knows its parent set (stride-2 coarser) derives its map from
+    the parent's map with pure index arithmetic (``pcgc_kernel_map_k3_from_parent``); only a root
+    set (the ~14 k-row bottleneck) is hashed.  A pruned set receives its map from ``pcgc_prune``."""
+
+    def __init__(self, keys: torch.Tensor, stride: int, parent=None, parent_of=None, info=None, nbr=None):
         self.keys, self.stride = keys, stride
-        self._table = self._nbr = None
+        self.parent, self.parent_of, self.info = parent, parent_of, info      # info None + parent => full octets
+        self._nbr = nbr
 
     def __len__(self):
         return self.keys.shape[0]
 
     @property
-    def table(self):
-        if self._table is None:
-            self._table = ops.HashTable(self.keys)
-        return self._table
-
-    @property
     def nbr(self):
         if self._nbr is None:
-            self._nbr = ops.kernel_map_k3(self.keys, self.table)
+            if self.parent is None:
+                self._nbr = ops.kernel_map_k3(self.keys, ops.HashTable(self.keys))
+            else:
+                self._nbr = ops.kernel_map_k3_from_parent(self.parent.nbr, len(self), self.keys, self.parent_of,
+                                                          self.info)
         return self._nbr
 
 
@@ -121,14 +124,24 @@ class Codec:
 
     def analysis(self, level0: _Level):
         """autoencoder.py:138-147 -> (y [N3,8], level3, [N2, N1, N0])."""
+        # coordinate pyramid first (integer work on keys only), so that the kernel maps can be
+        # derived top-down from the coarsest set
+        levels, down = [level0], []
+        for i in range(3):
+            pk, rows, off, parent_of = ops.stride_down(levels[-1].keys, keys_are_sorted=True, with_parent_of=True)
+            levels[-1].parent_of, levels[-1].info = parent_of, ops.parent_info(levels[-1].keys, off)
+            down.append((rows, off))
+            levels.append(_Level(pk, levels[-1].stride * 2))
+        for child, par in zip(levels[:-1], levels[1:]):
+            child.parent = par
         x = torch.ones((len(level0), 1), dtype=torch.float32, device=self.device)
         x = self._k3("encoder.conv0", x, level0, relu=True)
         level, sizes = level0, [len(level0)]
         for i in range(3):
-            pk, rows, off = ops.stride_down(level.keys, keys_are_sorted=True)
+            rows, off = down[i]
             x = ops.conv_k2s2(x, level.keys, rows, off, self.w[f"encoder.down{i}.kernel"],
                               self.w[f"encoder.down{i}.bias"], relu=True)
-            level = _Level(pk, level.stride * 2)
+            level = levels[i + 1]
             self._rec(f"encoder.down{i}", x, level)
             for j in range(3):
                 x = self._irn(f"encoder.block{i}.{j}", x, level)
@@ -141,7 +154,7 @@ class Codec:
         x, cls_list = y, []
         for i in range(3):
             x = ops.convT_k2s2(x, self.w[f"decoder.up{i}.kernel"], self.w[f"decoder.up{i}.bias"], relu=True)
-            level = _Level(ops.upsample_keys(level.keys), level.stride // 2)
+            level = _Level(ops.upsample_keys(level.keys), level.stride // 2, parent=level)    # full octets
             self._rec(f"decoder.up{i}", x, level)
             x = self._k3(f"decoder.conv{i}", x, level, relu=True)
             for j in range(3):
@@ -149,8 +162,12 @@ class Codec:
             cls = self._k3(f"decoder.conv{i}_cls", x, level)
             cls_list.append((cls, level))
             mask = ops.topk_mask(cls, min(len(level), int(nums[i])))
-            keys, x = ops.prune(mask, level.keys, x)
-            level = _Level(keys, level.stride)
+            if i < 2:                                       # the pruned set parents the next up-sampling
+                keys, x, nbr = ops.prune(mask, level.keys, x, nbr=level.nbr)
+                level = _Level(keys, level.stride, nbr=nbr)
+            else:
+                keys, x = ops.prune(mask, level.keys, x)
+                level = _Level(keys, level.stride)
         return level, x, cls_list
 
     # ---------------------------------------------------------------- codec

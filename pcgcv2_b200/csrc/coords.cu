@@ -131,10 +131,12 @@ __global__ void parent_heads_kernel(const uint64_t *__restrict__ sorted_keys, in
 
 __global__ void parent_emit_kernel(const uint64_t *__restrict__ sorted_keys, int64_t n,
                                    const int32_t *__restrict__ head_scan /* inclusive */,
-                                   uint64_t *__restrict__ parent_keys, int32_t *__restrict__ child_off,
-                                   int32_t *__restrict__ n_parents) {
+                                   const int32_t *__restrict__ child_rows, uint64_t *__restrict__ parent_keys,
+                                   int32_t *__restrict__ child_off, int32_t *__restrict__ n_parents,
+                                   int32_t *__restrict__ parent_of) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int32_t incl = head_scan[i];
+        if (parent_of) parent_of[child_rows[i]] = incl - 1;
         const bool is_head = (i == 0) || (incl != head_scan[i - 1]);
         if (is_head) {
             parent_keys[incl - 1] = parent_key(sorted_keys[i]);
@@ -144,6 +146,55 @@ __global__ void parent_emit_kernel(const uint64_t *__restrict__ sorted_keys, int
             child_off[incl] = (int32_t)n;
             *n_parents = incl;
         }
+    }
+}
+
+// info[p] = (first child row << 8) | 8-bit occupancy of the children of parent p (sorted children)
+__global__ void parent_info_kernel(const uint64_t *__restrict__ child_keys, const int32_t *__restrict__ child_off,
+                                   int64_t n_parents, uint64_t *__restrict__ info) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_parents; p += (int64_t)gridDim.x * blockDim.x) {
+        const int beg = child_off[p], end = child_off[p + 1];
+        uint32_t occ = 0;
+        for (int j = beg; j < end; ++j) occ |= 1u << (uint32_t)(child_keys[j] & 7);
+        info[p] = ((uint64_t)beg << 8) | occ;
+    }
+}
+
+// k=3 kernel map of a child set derived from its PARENT set's kernel map: no hashing.  A child at
+// position c in {0,1}^3 of parent p looks, for offset d in {-1,0,1}^3, into parent neighbour
+// floor((c+d)/2) at child position (c+d)&1.  Children are sorted (Morton), so the row of child c'
+// of parent p' is first_child(p') + popcount(occupancy(p') & ((1<<c')-1)); full-octet sets
+// (generative up-sampling output) need no tables at all: row = 8*p' + c'.
+__global__ void kernel_map_from_parent_kernel(const uint64_t *__restrict__ child_keys,
+                                              const int32_t *__restrict__ parent_of,
+                                              const uint64_t *__restrict__ info, const int32_t *__restrict__ pnbr,
+                                              int64_t n_parents, int64_t n, int32_t *__restrict__ nbr) {
+    const int k = blockIdx.y;
+    const int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
+    int32_t *__restrict__ out = nbr + (int64_t)k * n;
+    const bool full = (info == nullptr);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t r;
+        if (k == 13) {
+            r = (int32_t)i;
+        } else {
+            const int c = full ? (int)(i & 7) : (int)(child_keys[i] & 7);
+            const int64_t p = full ? (i >> 3) : (int64_t)parent_of[i];
+            const int tx = (c & 1) + dx, ty = ((c >> 1) & 1) + dy, tz = ((c >> 2) & 1) + dz;   // in {-1,0,1,2}
+            const int kp = ((tx >> 1) + 1) + 3 * ((ty >> 1) + 1) + 9 * ((tz >> 1) + 1);        // parent offset
+            const int cc = (tx & 1) | ((ty & 1) << 1) | ((tz & 1) << 2);                       // child position there
+            const int64_t q = kp == 13 ? p : (int64_t)__ldg(pnbr + (int64_t)kp * n_parents + p);
+            if (q < 0) {
+                r = -1;
+            } else if (full) {
+                r = (int32_t)(q * 8 + cc);
+            } else {
+                const uint64_t inf = __ldg(info + q);
+                const uint32_t occ = (uint32_t)(inf & 0xFF);
+                r = (occ >> cc) & 1 ? (int32_t)(inf >> 8) + __popc(occ & ((1u << cc) - 1)) : -1;
+            }
+        }
+        out[i] = r;
     }
 }
 
@@ -263,8 +314,8 @@ size_t pcgc_stride_down_ws_bytes(int64_t n) {
 }
 
 int pcgc_stride_down(const uint64_t *keys, int64_t n, int32_t keys_are_sorted, uint64_t *parent_keys,
-                     int32_t *n_parents, int32_t *child_rows, int32_t *child_off, void *ws, size_t ws_bytes,
-                     void *stream) {
+                     int32_t *n_parents, int32_t *child_rows, int32_t *child_off, int32_t *parent_of, void *ws,
+                     size_t ws_bytes, void *stream) {
     PCGC_REQUIRE(n >= 0 && n < 0x7FFFFFFF, "pcgc_stride_down: bad n");
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 0) {
@@ -298,8 +349,32 @@ int pcgc_stride_down(const uint64_t *keys, int64_t n, int32_t keys_are_sorted, u
     if ((rc = check_launch("parent_heads"))) return rc;
     PCGC_CUDA(cub::DeviceScan::InclusiveSum(scan_ws, scan_bytes, head, scan, n, s));
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    parent_emit_kernel<<<g, 256, 0, s>>>(sk, n, scan, parent_keys, child_off, n_parents);
+    parent_emit_kernel<<<g, 256, 0, s>>>(sk, n, scan, child_rows, parent_keys, child_off, n_parents, parent_of);
     return check_launch("parent_emit");
+}
+
+int pcgc_parent_info(const uint64_t *child_keys, const int32_t *child_off, int64_t n_parents, uint64_t *info,
+                     void *stream) {
+    PCGC_REQUIRE(n_parents >= 0, "pcgc_parent_info: bad n_parents");
+    if (n_parents == 0) return PCGC_OK;
+    parent_info_kernel<<<grid_for(n_parents, 256, 8), 256, 0, (cudaStream_t)stream>>>(child_keys, child_off, n_parents,
+                                                                                     info);
+    return check_launch("parent_info");
+}
+
+int pcgc_kernel_map_k3_from_parent(const uint64_t *child_keys, const int32_t *parent_of, const uint64_t *parent_info,
+                                   const int32_t *parent_nbr, int64_t n_parents, int64_t n, int32_t *nbr,
+                                   void *stream) {
+    PCGC_REQUIRE(n >= 0 && n < 0x7FFFFFFF && n_parents >= 0, "pcgc_kernel_map_k3_from_parent: bad sizes");
+    if (parent_info == nullptr)
+        PCGC_REQUIRE(n == 8 * n_parents, "pcgc_kernel_map_k3_from_parent: full-octet mode needs n == 8 * n_parents");
+    else
+        PCGC_REQUIRE(child_keys && parent_of, "pcgc_kernel_map_k3_from_parent: null child tables");
+    if (n == 0) return PCGC_OK;
+    dim3 grid(grid_for(n, 256, 2), 27);
+    kernel_map_from_parent_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(child_keys, parent_of, parent_info,
+                                                                         parent_nbr, n_parents, n, nbr);
+    return check_launch("kernel_map_from_parent");
 }
 
 int pcgc_upsample_keys(const uint64_t *keys, int64_t n, uint64_t *child_keys, void *stream) {

@@ -104,6 +104,19 @@ __global__ void prune_copy_kernel(const uint8_t *__restrict__ mask, int64_t n, c
     }
 }
 
+// kernel map of the pruned set = kernel map of the full set filtered through the same compaction
+__global__ void prune_map_kernel(const uint8_t *__restrict__ mask, int64_t n, const int32_t *__restrict__ pos,
+                                 const int32_t *__restrict__ nbr_in, const int32_t *__restrict__ n_kept,
+                                 int32_t *__restrict__ nbr_out) {
+    const int k = blockIdx.y;
+    const int64_t stride_out = *n_kept;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!mask[i]) continue;
+        const int32_t v = nbr_in[(int64_t)k * n + i];
+        nbr_out[(int64_t)k * stride_out + pos[i]] = (v >= 0 && mask[v]) ? pos[v] : -1;
+    }
+}
+
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static size_t scan_temp_bytes(int64_t n) {
     size_t b = 0;
@@ -165,8 +178,8 @@ size_t pcgc_prune_ws_bytes(int64_t n) {
 }
 
 int pcgc_prune(const uint8_t *mask, int64_t n, const uint64_t *keys, const float *feats, int32_t ld, int32_t channels,
-               uint64_t *keys_out, float *feats_out, int32_t out_ld, int32_t *n_kept, void *ws, size_t ws_bytes,
-               void *stream) {
+               uint64_t *keys_out, float *feats_out, int32_t out_ld, int32_t *n_kept, const int32_t *nbr_in,
+               int32_t *nbr_out, void *ws, size_t ws_bytes, void *stream) {
     PCGC_REQUIRE(n >= 0 && n < 0x7FFFFFFF && channels >= 1 && ld >= channels && out_ld >= channels, "pcgc_prune: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 0) {
@@ -192,7 +205,13 @@ int pcgc_prune(const uint8_t *mask, int64_t n, const uint64_t *keys, const float
     const int64_t total = n * (vec ? channels / 4 : channels);
     prune_copy_kernel<<<grid_for(total, 256, 8), 256, 0, s>>>(mask, n, pos, keys, feats, ld, channels, keys_out,
                                                              feats_out, out_ld, n_kept, vec);
-    return check_launch("prune_copy");
+    if ((rc = check_launch("prune_copy"))) return rc;
+    if (nbr_in && nbr_out) {
+        dim3 grid(grid_for(n, 256, 2), 27);
+        prune_map_kernel<<<grid, 256, 0, s>>>(mask, n, pos, nbr_in, n_kept, nbr_out);
+        rc = check_launch("prune_map");
+    }
+    return rc;
 }
 
 }  // extern "C"

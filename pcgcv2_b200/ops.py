@@ -99,8 +99,9 @@ def kernel_map_k3(keys: torch.Tensor, table: HashTable, count_pairs=False):
     return (nbr, npairs) if count_pairs else nbr
 
 
-def stride_down(keys: torch.Tensor, keys_are_sorted=False):
-    """-> (parent_keys [P], child_rows int32 [N], child_off int32 [P+1]); one sync for P."""
+def stride_down(keys: torch.Tensor, keys_are_sorted=False, with_parent_of=False):
+    """-> (parent_keys [P], child_rows int32 [N], child_off int32 [P+1][, parent_of int32 [N]]);
+    one sync for P."""
     n = keys.shape[0]
     L = _lib.lib()
     dev = keys.device
@@ -108,12 +109,32 @@ def stride_down(keys: torch.Tensor, keys_are_sorted=False):
     n_par = torch.zeros(1, dtype=torch.int32, device=dev)
     rows = torch.empty(n, dtype=torch.int32, device=dev)
     off = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    parent_of = torch.empty(n, dtype=torch.int32, device=dev) if with_parent_of else None
     nbytes = L.pcgc_stride_down_ws_bytes(n)
     ws = _ws(nbytes, dev)
-    check(L.pcgc_stride_down(_p(keys), n, int(bool(keys_are_sorted)), _p(parent), _p(n_par), _p(rows), _p(off), _p(ws),
-                             nbytes, _stream()), "pcgc_stride_down")
+    check(L.pcgc_stride_down(_p(keys), n, int(bool(keys_are_sorted)), _p(parent), _p(n_par), _p(rows), _p(off),
+                             _p(parent_of), _p(ws), nbytes, _stream()), "pcgc_stride_down")
     p = int(n_par.item())
+    if with_parent_of:
+        return parent[:p], rows, off[:p + 1], parent_of
     return parent[:p], rows, off[:p + 1]
+
+
+def parent_info(child_keys: torch.Tensor, child_off: torch.Tensor) -> torch.Tensor:
+    """per parent: (first child row << 8) | occupancy byte (children sorted)."""
+    n_par = child_off.shape[0] - 1
+    info = torch.empty(n_par, dtype=torch.int64, device=child_keys.device)
+    check(_lib.lib().pcgc_parent_info(_p(child_keys), _p(child_off), n_par, _p(info), _stream()), "pcgc_parent_info")
+    return info
+
+
+def kernel_map_k3_from_parent(parent_nbr: torch.Tensor, n: int, child_keys=None, parent_of=None, info=None):
+    """child kernel map [27, n] from the parent's [27, P]; info=None: full octets (n == 8 P)."""
+    n_par = parent_nbr.shape[1]
+    nbr = torch.empty((27, n), dtype=torch.int32, device=parent_nbr.device)
+    check(_lib.lib().pcgc_kernel_map_k3_from_parent(_p(child_keys), _p(parent_of), _p(info), _p(parent_nbr), n_par, n,
+                                                    _p(nbr), _stream()), "pcgc_kernel_map_k3_from_parent")
+    return nbr
 
 
 def upsample_keys(keys: torch.Tensor) -> torch.Tensor:
@@ -222,8 +243,8 @@ def topk_mask(logits: torch.Tensor, k: int) -> torch.Tensor:
     return mask.bool()
 
 
-def prune(mask: torch.Tensor, keys, feats):
-    """stable compaction -> (keys_kept, feats_kept); one sync for the count."""
+def prune(mask: torch.Tensor, keys, feats, nbr=None):
+    """stable compaction -> (keys_kept, feats_kept[, nbr_kept]); one sync for the count."""
     feats = _feat(feats)
     n, c = feats.shape
     L = _lib.lib()
@@ -235,9 +256,12 @@ def prune(mask: torch.Tensor, keys, feats):
     n_kept = torch.zeros(1, dtype=torch.int32, device=dev)
     nbytes = L.pcgc_prune_ws_bytes(n)
     ws = _ws(nbytes, dev)
+    nbr_out = torch.empty(27 * n, dtype=torch.int32, device=dev) if nbr is not None else None
     check(L.pcgc_prune(_p(m8), n, _p(keys), _p(feats), feats.stride(0), c, _p(keys_out), _p(feats_out), c, _p(n_kept),
-                       _p(ws), nbytes, _stream()), "pcgc_prune")
+                       _p(nbr), _p(nbr_out), _p(ws), nbytes, _stream()), "pcgc_prune")
     k = int(n_kept.item())
+    if nbr is not None:
+        return (None if keys is None else keys_out[:k]), feats_out[:k], nbr_out[:27 * k].view(27, k)
     return (None if keys is None else keys_out[:k]), feats_out[:k]
 
 

@@ -128,6 +128,36 @@ def test_stride_down_map(presorted):
     assert ((keys.cpu().numpy() & 7) == kidx_ref).all()
 
 
+@pytest.mark.parametrize("batch", [1, 3])
+def test_kernel_map_from_parent_equals_hashed_map(batch):
+    """hierarchical derivation (no hashing) == hash-probed map, for partial and full octets."""
+    c = _surface()
+    if batch > 1:
+        c[:, 0] = np.random.default_rng(0).integers(0, batch, size=len(c))
+    keys, _ = ops.argsort_u64(_keys(c))
+    pk, rows, off, parent_of = ops.stride_down(keys, keys_are_sorted=True, with_parent_of=True)
+    info = ops.parent_info(keys, off)
+    pnbr = ops.kernel_map_k3(pk, ops.HashTable(pk))
+    want = ops.kernel_map_k3(keys, ops.HashTable(keys))
+    got = ops.kernel_map_k3_from_parent(pnbr, len(keys), keys, parent_of, info)
+    assert torch.equal(got, want)
+    up = ops.upsample_keys(keys)                                # full octets: 8 children per row
+    want = ops.kernel_map_k3(up, ops.HashTable(up))
+    assert torch.equal(ops.kernel_map_k3_from_parent(ops.kernel_map_k3(keys, ops.HashTable(keys)), len(up)), want)
+
+
+def test_prune_filters_kernel_map():
+    c = _surface()
+    keys, _ = ops.argsort_u64(_keys(c))
+    nbr = ops.kernel_map_k3(keys, ops.HashTable(keys))
+    g = torch.Generator().manual_seed(1)
+    mask = (torch.rand(len(keys), generator=g) < 0.5).to(DEV)
+    f = torch.randn(len(keys), 8, generator=g).to(DEV)
+    k2, f2, nbr2 = ops.prune(mask, keys, f, nbr=nbr)
+    assert torch.equal(nbr2, ops.kernel_map_k3(k2, ops.HashTable(k2)))
+    assert torch.equal(f2, f[mask])
+
+
 def test_upsample_keys():
     c = _cloud(7, n=500, size=10, batch=2, stride=4)
     child = ops.unpack_keys(ops.upsample_keys(_keys(c, 4)), 2).cpu().numpy()
