@@ -130,6 +130,15 @@ int pcgc_argsort_u64(const uint64_t *keys, int64_t n, int end_bit, uint64_t *key
 int pcgc_conv_k3_fwd(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, const float *weight,
                      const float *bias, int32_t cin, int32_t cout, const float *residual,
                      int32_t res_ld, float *out, int32_t out_ld, int32_t flags, void *stream);
+/* a3 on the tensor cores (3xTF32, FP32-accurate): the same convolution with the weights
+ * pre-packed ONCE per layer into mma B-fragment order.  pcgc_conv_k3_packed_floats returns the
+ * packed size (0 = this cin x cout has no tensor-core kernel: cin in {8,16,32,64}, cout in
+ * {1,4,8,16,32,64}); input rows must be 16-byte aligned. */
+size_t pcgc_conv_k3_packed_floats(int32_t cin, int32_t cout);
+int pcgc_conv_k3_pack_weights(const float *weight, int32_t cin, int32_t cout, float *packed, void *stream);
+int pcgc_conv_k3_fwd_packed(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, const float *packed,
+                            const float *bias, int32_t cin, int32_t cout, const float *residual,
+                            int32_t res_ld, float *out, int32_t out_ld, int32_t flags, void *stream);
 /* a7  ME.MinkowskiConvolution(kernel_size=1) == F.mm(kernel) + bias. */
 int pcgc_conv_k1_fwd(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias,
                      int32_t cin, int32_t cout, const float *residual, int32_t res_ld, float *out,

@@ -48,6 +48,9 @@ SIGNATURES = {
     "pcgc_argsort_ws_bytes": (c_sz, [c_i64]),
     "pcgc_argsort_u64": (ctypes.c_int, [c_p, c_i64, ctypes.c_int, c_p, c_p, c_p, c_sz, c_p]),
     "pcgc_conv_k3_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),
+    "pcgc_conv_k3_packed_floats": (c_sz, [c_i32, c_i32]),
+    "pcgc_conv_k3_pack_weights": (ctypes.c_int, [c_p, c_i32, c_i32, c_p, c_p]),
+    "pcgc_conv_k3_fwd_packed": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),
     "pcgc_conv_k1_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),
     "pcgc_conv_k2s2_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_i32, c_p]),
     "pcgc_convT_k2s2_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_i32, c_p]),

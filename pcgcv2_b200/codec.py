@@ -63,7 +63,7 @@ class _Level:
 
 
 class Codec:
-    def __init__(self, state_dict, device="cuda"):
+    def __init__(self, state_dict, device="cuda", use_tensor_cores=True):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("pcgcv2_b200.Codec runs on a CUDA device only (there is no CPU path)")
@@ -72,6 +72,14 @@ class Codec:
         g = lambda name: [state_dict[f"entropy_bottleneck.{name}.{i}"] for i in range(4)]
         self.eb_params = ops.pack_eb_params(g("_matrices"), g("_biases"), g("_factors"), self.device)
         self.channels = self.eb_params.shape[0]
+        # k=3 weights pre-packed for the tensor-core kernel where one exists (cin >= 8)
+        self.packed = {}
+        if use_tensor_cores:
+            for k, v in self.w.items():
+                if k.endswith(".kernel") and v.dim() == 3 and v.shape[0] == 27:
+                    pw = ops.PackedK3(v)
+                    if pw.packed is not None:
+                        self.packed[k[:-len(".kernel")]] = pw
         self.record = None              # set to a dict to capture per-layer activations (parity tests)
         self.probe = {}                 # layer name -> list of (start, end) CUDA event pairs (bench.py roofline)
 
@@ -87,8 +95,12 @@ class Codec:
             nbr = level.nbr                                    # keep the (cached) map build outside the probe
             start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             start.record()
-        y = ops.conv_k3(x, level.nbr, self.w[name + ".kernel"], self.w[name + ".bias"], residual=residual, relu=relu,
-                        out=out)
+        pw = self.packed.get(name)
+        if pw is not None and x.stride(0) % 4 == 0:
+            y = ops.conv_k3_packed(x, level.nbr, pw, self.w[name + ".bias"], residual=residual, relu=relu, out=out)
+        else:
+            y = ops.conv_k3(x, level.nbr, self.w[name + ".kernel"], self.w[name + ".bias"], residual=residual,
+                            relu=relu, out=out)
         if ev is not None:
             end.record()
             ev.append((start, end))

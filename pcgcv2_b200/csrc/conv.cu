@@ -2,6 +2,7 @@
 // (SURVEY section 8 rows a3, a5, a6, a7).
 #include "common.cuh"
 #include "conv_dispatch.h"
+#include "conv_mma.cuh"
 
 namespace pcgc {
 
@@ -101,6 +102,37 @@ int pcgc_conv_k3_fwd(const float *in, int32_t in_ld, const int32_t *nbr, int64_t
     conv_generic_kernel<<<grid_for(n * cout, 256, 8), 256, 0, s>>>(in, in_ld, nbr, n, 27, weight, bias, cin, cout,
                                                                    residual, res_ld, out, out_ld, flags);
     return check_launch("conv_generic");
+}
+
+size_t pcgc_conv_k3_packed_floats(int32_t cin, int32_t cout) {
+    const bool ok = (cin == 8 || cin == 16 || cin == 32 || cin == 64) &&
+                    (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32 || cout == 64);
+    return ok ? (size_t)27 * (cin / 8) * ((cout + 7) / 8) * 64 : 0;
+}
+
+int pcgc_conv_k3_pack_weights(const float *weight, int32_t cin, int32_t cout, float *packed, void *stream) {
+    const size_t total = pcgc_conv_k3_packed_floats(cin, cout);
+    PCGC_REQUIRE(total > 0 && weight && packed, "pcgc_conv_k3_pack_weights: no tensor-core kernel for %dx%d", cin, cout);
+    pack_weights_mma_kernel<<<grid_for((int64_t)total, 256, 4), 256, 0, (cudaStream_t)stream>>>(weight, 27, cin, cout, packed);
+    return check_launch("pack_weights_mma");
+}
+
+int pcgc_conv_k3_fwd_packed(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, const float *packed,
+                            const float *bias, int32_t cin, int32_t cout, const float *residual, int32_t res_ld,
+                            float *out, int32_t out_ld, int32_t flags, void *stream) {
+    int rc = check_conv_args("pcgc_conv_k3_fwd_packed", in, packed, out, n, cin, cout, in_ld, out_ld);
+    if (rc || n == 0) return rc;
+    PCGC_REQUIRE(nbr != nullptr, "pcgc_conv_k3_fwd_packed: null kernel map");
+    PCGC_REQUIRE(pcgc_conv_k3_packed_floats(cin, cout) > 0, "pcgc_conv_k3_fwd_packed: no tensor-core kernel for %dx%d", cin, cout);
+    PCGC_REQUIRE((in_ld % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)packed & 15) == 0),
+                 "pcgc_conv_k3_fwd_packed: input rows must be 16-byte aligned (ld %% 4 == 0)");
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = kNotHandled;
+#define CASE(CI) if (cin == CI) rc = mma_ci##CI(in, in_ld, nbr, n, packed, bias, cout, residual, res_ld, out, out_ld, flags, s);
+    PCGC_FOR_CI(CASE)
+#undef CASE
+    PCGC_REQUIRE(rc != kNotHandled, "pcgc_conv_k3_fwd_packed: unsupported shape %dx%d", cin, cout);
+    return rc;
 }
 
 int pcgc_conv_k1_fwd(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias, int32_t cin,

@@ -11,6 +11,8 @@ constexpr int kNotHandled = 1;
 #define PCGC_DECL(CI)                                                                                              \
     int k3_ci##CI(const float *in, int in_ld, const int32_t *nbr, int64_t n, const float *w, const float *b,      \
                   int cout, const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s);      \
+    int mma_ci##CI(const float *in, int in_ld, const int32_t *nbr, int64_t n, const float *packed, const float *b, \
+                   int cout, const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s);    \
     int k1_ci##CI(const float *in, int in_ld, int64_t n, const float *w, const float *b, int cout,                \
                   const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s);                \
     int down_ci##CI(const float *in, int in_ld, const uint64_t *keys, const int32_t *rows, const int32_t *off,    \

@@ -5,6 +5,7 @@
 #endif
 #include "conv_rowlane.cuh"
 #include "conv_tile.cuh"
+#include "conv_mma.cuh"
 #include "conv_dispatch.h"
 
 namespace pcgc {
@@ -131,6 +132,23 @@ static int up_case(const float *in, int in_ld, int64_t n_in, const float *w, con
     return kNotHandled;
 }
 
+template <int CO>
+static int mma_case(const float *in, int in_ld, const int32_t *nbr, int64_t n, const float *packed, const float *b,
+                    const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s) {
+    if constexpr ((CI == 8 || CI == 16 || CI == 32 || CI == 64) && CO <= 64) {
+        using C = MmaCfg<CI, CO>;
+        const size_t smem = C::smem_bytes();
+        auto kern = conv_k3_mma_kernel<CI, CO>;
+        int rc = prepare_smem(kern, smem);
+        if (rc) return rc;
+        const int ctas = smem <= 32 * 1024 ? 3 : (smem <= 100 * 1024 ? 2 : 1);
+        kern<<<grid_for(n, C::ROWS_PER_CTA, ctas), C::THREADS, smem, s>>>(in, in_ld, nbr, n, packed, b, res, res_ld, out,
+                                                                         out_ld, flags);
+        return check_launch("conv_k3_mma");
+    }
+    return kNotHandled;
+}
+
 #define PCGC_FOR_CO(X) X(1) X(4) X(8) X(16) X(32) X(64) X(128)
 #define PCGC_CAT2(a, b) a##b
 #define PCGC_CAT(a, b) PCGC_CAT2(a, b)
@@ -138,6 +156,15 @@ static int up_case(const float *in, int in_ld, int64_t n_in, const float *w, con
 int PCGC_CAT(k3_ci, PCGC_CI)(const float *in, int in_ld, const int32_t *nbr, int64_t n, const float *w, const float *b,
                              int cout, const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s) {
 #define CASE(CO) if (cout == CO) return k3_case<CO>(in, in_ld, nbr, n, w, b, res, res_ld, out, out_ld, flags, s);
+    PCGC_FOR_CO(CASE)
+#undef CASE
+    return kNotHandled;
+}
+
+int PCGC_CAT(mma_ci, PCGC_CI)(const float *in, int in_ld, const int32_t *nbr, int64_t n, const float *packed,
+                              const float *b, int cout, const float *res, int res_ld, float *out, int out_ld,
+                              int flags, cudaStream_t s) {
+#define CASE(CO) if (cout == CO) return mma_case<CO>(in, in_ld, nbr, n, packed, b, res, res_ld, out, out_ld, flags, s);
     PCGC_FOR_CO(CASE)
 #undef CASE
     return kNotHandled;

@@ -202,6 +202,35 @@ def test_conv_k3_vs_oracle(cin, cout):
         assert (wide[:, :4] == -7).all() and (wide[:, 4 + cout:] == -7).all()
 
 
+@pytest.mark.parametrize("cin,cout", [(8, 16), (8, 8), (16, 16), (16, 4), (16, 1), (16, 32), (32, 8), (32, 32),
+                                      (32, 1), (64, 16), (64, 64), (64, 1), (64, 32), (32, 64)])
+def test_conv_k3_tensor_core_vs_oracle(cin, cout):
+    """3xTF32 mma.sync kernel keeps FP32 accuracy (same tolerance as the FFMA kernels)."""
+    c = _surface()[:20011]
+    keys = _keys(c)
+    nbr = ops.kernel_map_k3(keys, ops.HashTable(keys))
+    g = torch.Generator().manual_seed(cin * 3 + cout)
+    f = torch.randn(len(c), cin, generator=g)
+    w = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    b = torch.randn(1, cout, generator=g)
+    ref = S.conv_k3(f, c, 1, w, b)
+    pw = ops.PackedK3(w.to(DEV))
+    assert pw.packed is not None
+    got = ops.conv_k3_packed(f.to(DEV), nbr, pw, b.to(DEV))
+    assert _rel_err(got, ref) < CONV_TOL
+    if cout % 4 == 0:
+        res = torch.randn(len(c), cout, generator=g)
+        wide = torch.full((len(c), cout + 8), -7.0, device=DEV)
+        ops.conv_k3_packed(f.to(DEV), nbr, pw, b.to(DEV), residual=res.to(DEV), relu=True, out=wide[:, 4:4 + cout])
+        assert _rel_err(wide[:, 4:4 + cout], torch.relu(ref + res)) < CONV_TOL
+        assert (wide[:, :4] == -7).all() and (wide[:, 4 + cout:] == -7).all()
+    for n in (1, 15, 17, 129):                                  # tile tails
+        kk = _keys(c[:n])
+        nb = ops.kernel_map_k3(kk, ops.HashTable(kk))
+        got = ops.conv_k3_packed(f[:n].to(DEV), nb, pw, b.to(DEV))
+        assert _rel_err(got, S.conv_k3(f[:n], c[:n], 1, w, b)) < CONV_TOL
+
+
 def test_conv_k3_surface_and_ragged_sizes():
     c = _surface()
     keys = _keys(c)
