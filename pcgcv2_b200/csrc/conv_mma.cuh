@@ -165,9 +165,16 @@ conv_k3_mma_kernel(const float *__restrict__ in, int in_ld, const int32_t *__res
                         uint32_t bh0, bl0, bh1, bl1;
                         split_tf32(w.x, bh0, bl0);
                         split_tf32(w.y, bh1, bl1);
-                        mma_tf32(acc[j], al, bh0, bh1);
-                        mma_tf32(acc[j], ah, bl0, bl1);
-                        mma_tf32(acc[j], ah, bh0, bh1);
+                        // The tensor core adds into its accumulator with truncation (a biased ~2^-23 relative
+                        // error per MMA).  Chaining all 27*KS*3 MMAs of a row into one accumulator let that bias
+                        // grow to ~2e-5 per layer (measured), so each 3-MMA group sums into a zeroed temporary
+                        // and joins the running sum through a round-to-nearest FADD.
+                        float part[4] = {0.f, 0.f, 0.f, 0.f};
+                        mma_tf32(part, al, bh0, bh1);
+                        mma_tf32(part, ah, bl0, bl1);
+                        mma_tf32(part, ah, bh0, bh1);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[j][e] += part[e];
                     }
                 }
             }
