@@ -107,13 +107,13 @@ int pcgc_conv_k3_fwd(const float *in, int32_t in_ld, const int32_t *nbr, int64_t
 size_t pcgc_conv_k3_packed_floats(int32_t cin, int32_t cout) {
     const bool ok = (cin == 8 || cin == 16 || cin == 32 || cin == 64) &&
                     (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32 || cout == 64);
-    return ok ? (size_t)27 * (cin / 8) * ((cout + 7) / 8) * 64 : 0;
+    return ok ? (size_t)27 * (cin / 8) * ((cout + 15) / 16) * 256 : 0;
 }
 
 int pcgc_conv_k3_pack_weights(const float *weight, int32_t cin, int32_t cout, float *packed, void *stream) {
     const size_t total = pcgc_conv_k3_packed_floats(cin, cout);
     PCGC_REQUIRE(total > 0 && weight && packed, "pcgc_conv_k3_pack_weights: no tensor-core kernel for %dx%d", cin, cout);
-    pack_weights_mma_kernel<<<grid_for((int64_t)total, 256, 4), 256, 0, (cudaStream_t)stream>>>(weight, 27, cin, cout, packed);
+    pack_weights_mma_kernel<<<grid_for((int64_t)total / 2, 256, 4), 256, 0, (cudaStream_t)stream>>>(weight, 27, cin, cout, packed);
     return check_launch("pack_weights_mma");
 }
 

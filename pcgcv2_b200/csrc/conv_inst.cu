@@ -141,7 +141,12 @@ static int mma_case(const float *in, int in_ld, const int32_t *nbr, int64_t n, c
         auto kern = conv_k3_mma_kernel<CI, CO>;
         int rc = prepare_smem(kern, smem);
         if (rc) return rc;
-        const int ctas = smem <= 32 * 1024 ? 3 : (smem <= 100 * 1024 ? 2 : 1);
+        static int ctas = 0;                               // resident CTAs per SM of this instantiation
+        if (ctas == 0) {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+            ctas = nb;
+        }
         kern<<<grid_for(n, C::ROWS_PER_CTA, ctas), C::THREADS, smem, s>>>(in, in_ld, nbr, n, packed, b, res, res_ld, out,
                                                                          out_ld, flags);
         return check_launch("conv_k3_mma");
