@@ -173,12 +173,13 @@ class Codec:
                 x = self._irn(f"decoder.block{i}.{j}", x, level)
             cls = self._k3(f"decoder.conv{i}_cls", x, level)
             cls_list.append((cls, level))
-            mask = ops.topk_mask(cls, min(len(level), int(nums[i])))
+            k = min(len(level), int(nums[i]))
+            mask = ops.topk_mask(cls, k)                    # exactly k rows survive: no size read-back needed
             if i < 2:                                       # the pruned set parents the next up-sampling
-                keys, x, nbr = ops.prune(mask, level.keys, x, nbr=level.nbr)
+                keys, x, nbr = ops.prune(mask, level.keys, x, nbr=level.nbr, n_kept_hint=k)
                 level = _Level(keys, level.stride, nbr=nbr)
             else:
-                keys, x = ops.prune(mask, level.keys, x)
+                keys, x = ops.prune(mask, level.keys, x, n_kept_hint=k)
                 level = _Level(keys, level.stride)
         return level, x, cls_list
 

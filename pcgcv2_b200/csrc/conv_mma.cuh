@@ -27,21 +27,41 @@
 
 namespace pcgc {
 
+// tuning defaults: RG = 8-row groups per warp, BATCH = offsets gathered ahead of the math
 template <int CIN, int COUT>
+struct MmaTune {
+    static constexpr int MT = (COUT + 15) / 16;
+    // measured on B200 with tools/run_variants.sh on the 1.69 M-row decoder level (profiles/r01_conv_variants.txt)
+    static constexpr int RG = (MT >= 2 || CIN >= 64) ? 2 : 4;
+    static constexpr int BATCH = (CIN <= 16) ? 3 : 1;
+    static constexpr int MINB = CIN <= 32 ? 2 : 1;                    // min CTAs/SM handed to the register allocator
+    // weights resident in smem when all 27 offsets (hi+lo) fit with 2 CTAs/SM; else streamed per batch
+    static constexpr int RES = ((size_t)27 * (CIN / 8) * MT * 256 * 4 <= 112 * 1024) && !(CIN == 16 && MT == 2) ? 1 : 0;
+};
+
+template <int CIN, int COUT, int RG_ = MmaTune<CIN, COUT>::RG, int BATCH_ = MmaTune<CIN, COUT>::BATCH,
+          int RES_ = MmaTune<CIN, COUT>::RES>
 struct MmaCfg {
     static_assert(CIN == 8 || CIN % 16 == 0, "mma kernel: CIN must be 8 or a multiple of 16");
+    static_assert(27 % BATCH_ == 0, "BATCH must divide 27");
     static constexpr int KS = CIN / 8;                        // k-steps (8 channels) per offset
     static constexpr int MT = (COUT + 15) / 16;               // m-tiles (16 output channels)
     static constexpr int CHUNKS = CIN >= 16 ? CIN / 16 : 1;   // loads per gathered row per lane
     static constexpr int AV = CIN >= 16 ? 4 : 2;              // floats per load
-    static constexpr int RG = MT >= 2 ? 2 : 4;                // 8-row groups per warp
-    static constexpr int BATCH = (CIN * RG <= 64) ? 3 : 1;    // offsets gathered ahead of the math
+    static constexpr int RG = RG_;
+    static constexpr int BATCH = BATCH_;
     static constexpr int W_OFF = KS * MT * 256;               // packed floats per offset (hi + lo quads)
     static constexpr int THREADS = 256;
     static constexpr int ROWS_PER_WARP = 8 * RG;
     static constexpr int ROWS_PER_CTA = (THREADS / 32) * ROWS_PER_WARP;
-    static constexpr bool RESIDENT = (size_t)27 * W_OFF * 4 <= 112 * 1024;   // two CTAs per SM still fit
-    static constexpr size_t smem_bytes() { return RESIDENT ? (size_t)27 * W_OFF * 4 : (size_t)2 * BATCH * W_OFF * 4; }
+    static constexpr bool RESIDENT = RES_ != 0;
+    // tile's kernel-map slice staged in smem unless big resident weights leave no room for 2 CTAs/SM
+    static constexpr bool IDX_SMEM = !(RESIDENT && (size_t)27 * W_OFF * 4 > 64 * 1024);
+    static constexpr size_t weight_smem_floats() { return RESIDENT ? (size_t)27 * W_OFF : (size_t)2 * BATCH * W_OFF; }
+    // + the tile's slice of the kernel map, [27][ROWS_PER_WARP] int32 per warp (loaded coalesced once per tile)
+    static constexpr size_t smem_bytes() {
+        return weight_smem_floats() * 4 + (IDX_SMEM ? (size_t)(THREADS / 32) * 27 * ROWS_PER_WARP * 4 : 0);
+    }
     static constexpr size_t packed_floats() { return (size_t)27 * W_OFF; }
 };
 
@@ -96,15 +116,17 @@ __device__ __forceinline__ void mma_tf32_zero(float (&d)[4], const float4 &a, fl
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(256)
+template <int CIN, int COUT, int RG_ = MmaTune<CIN, COUT>::RG, int BATCH_ = MmaTune<CIN, COUT>::BATCH,
+          int MINB = MmaTune<CIN, COUT>::MINB, int RES_ = MmaTune<CIN, COUT>::RES>
+__global__ void __launch_bounds__(256, MINB)
 conv_k3_mma_kernel(const float *__restrict__ in, int in_ld, const int32_t *__restrict__ nbr, int64_t n,
                    const float *__restrict__ packed, const float *__restrict__ bias,
                    const float *__restrict__ residual, int res_ld, float *__restrict__ out, int out_ld, int flags) {
-    using C = MmaCfg<CIN, COUT>;
+    using C = MmaCfg<CIN, COUT, RG_, BATCH_, RES_>;
     constexpr int KS = C::KS, MT = C::MT, CHUNKS = C::CHUNKS, AV = C::AV, RG = C::RG, W_OFF = C::W_OFF, B = C::BATCH;
     extern __shared__ __align__(16) float wsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    int32_t *idx_s = reinterpret_cast<int32_t *>(wsm + C::weight_smem_floats()) + warp * 27 * C::ROWS_PER_WARP;
 
     if constexpr (C::RESIDENT) {                        // all 27 offsets stay in shared memory
         for (int i = threadIdx.x; i < 27 * W_OFF / 4; i += C::THREADS) cp_async16(wsm + 4 * i, packed + 4 * i, true);
@@ -133,6 +155,17 @@ conv_k3_mma_kernel(const float *__restrict__ in, int in_ld, const int32_t *__res
             __syncthreads();                             // previous tile's readers are done with both buffers
             stage_weights(0, 0);
         }
+        // this warp's slice of the kernel map: 27 coalesced loads, no dependent index load per offset later
+        if constexpr (C::IDX_SMEM) {
+            __syncwarp();
+            for (int i = lane; i < 27 * C::ROWS_PER_WARP; i += 32) {
+                const int k = i / C::ROWS_PER_WARP, rr = i % C::ROWS_PER_WARP;
+                idx_s[i] = row0 + rr < n ? __ldg(nbr + (int64_t)k * n + row0 + rr) : -1;
+            }
+            __syncwarp();
+        }
+        const char *in_lane = reinterpret_cast<const char *>(in + (AV == 4 ? 4 * t : 2 * t));
+        const int64_t ld_bytes = (int64_t)in_ld * 4;
 #pragma unroll 1
         for (int batch = 0; batch < 27 / B; ++batch) {
             // ---- gather: lane loads its piece of the neighbour row of output row 8*r + g, for every group r
@@ -141,8 +174,12 @@ conv_k3_mma_kernel(const float *__restrict__ in, int in_ld, const int32_t *__res
             for (int o = 0; o < B; ++o)
 #pragma unroll
                 for (int r = 0; r < RG; ++r) {
-                    const int64_t row = row0 + 8 * r + g;
-                    idx[o][r] = row < n ? __ldg(nbr + (int64_t)(batch * B + o) * n + row) : -1;
+                    if constexpr (C::IDX_SMEM) {
+                        idx[o][r] = idx_s[(batch * B + o) * C::ROWS_PER_WARP + 8 * r + g];
+                    } else {
+                        const int64_t row = row0 + 8 * r + g;
+                        idx[o][r] = row < n ? __ldg(nbr + (int64_t)(batch * B + o) * n + row) : -1;
+                    }
                 }
             float x[B][RG][CHUNKS][AV];
 #pragma unroll
@@ -151,14 +188,13 @@ conv_k3_mma_kernel(const float *__restrict__ in, int in_ld, const int32_t *__res
                 for (int r = 0; r < RG; ++r)
 #pragma unroll
                     for (int q = 0; q < CHUNKS; ++q) {
-                        const float *src = in + (int64_t)idx[o][r] * in_ld + (AV == 4 ? 16 * q + 4 * t : 2 * t);
+                        const char *src = in_lane + idx[o][r] * ld_bytes + 64 * q;
+                        const bool ok = idx[o][r] >= 0;
                         if constexpr (AV == 4) {
-                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (idx[o][r] >= 0) v = __ldg(reinterpret_cast<const float4 *>(src));
+                            const float4 v = ok ? __ldg(reinterpret_cast<const float4 *>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
                             x[o][r][q][0] = v.x; x[o][r][q][1] = v.y; x[o][r][q][2] = v.z; x[o][r][q][3] = v.w;
                         } else {
-                            float2 v = make_float2(0.f, 0.f);
-                            if (idx[o][r] >= 0) v = __ldg(reinterpret_cast<const float2 *>(src));
+                            const float2 v = ok ? __ldg(reinterpret_cast<const float2 *>(src)) : make_float2(0.f, 0.f);
                             x[o][r][q][0] = v.x; x[o][r][q][1] = v.y;
                         }
                     }

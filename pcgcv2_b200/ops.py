@@ -269,8 +269,9 @@ def topk_mask(logits: torch.Tensor, k: int) -> torch.Tensor:
     return mask.bool()
 
 
-def prune(mask: torch.Tensor, keys, feats, nbr=None):
-    """stable compaction -> (keys_kept, feats_kept[, nbr_kept]); one sync for the count."""
+def prune(mask: torch.Tensor, keys, feats, nbr=None, n_kept_hint=None):
+    """stable compaction -> (keys_kept, feats_kept[, nbr_kept]); one sync for the count unless the
+    caller already knows it (``n_kept_hint``: e.g. an exact top-k mask keeps exactly k rows)."""
     feats = _feat(feats)
     n, c = feats.shape
     L = _lib.lib()
@@ -285,7 +286,7 @@ def prune(mask: torch.Tensor, keys, feats, nbr=None):
     nbr_out = torch.empty(27 * n, dtype=torch.int32, device=dev) if nbr is not None else None
     check(L.pcgc_prune(_p(m8), n, _p(keys), _p(feats), feats.stride(0), c, _p(keys_out), _p(feats_out), c, _p(n_kept),
                        _p(nbr), _p(nbr_out), _p(ws), nbytes, _stream()), "pcgc_prune")
-    k = int(n_kept.item())
+    k = int(n_kept.item()) if n_kept_hint is None else int(n_kept_hint)
     if nbr is not None:
         return (None if keys is None else keys_out[:k]), feats_out[:k], nbr_out[:27 * k].view(27, k)
     return (None if keys is None else keys_out[:k]), feats_out[:k]

@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--shapes", default="16x16")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--ffma", action="store_true")
+ap.add_argument("--dump", default="")
 args = ap.parse_args()
 cache = "/tmp/vox10_seed0.npy"
 pts = np.load(cache) if os.path.exists(cache) else synth.synthetic_vox10(0)
@@ -28,6 +29,10 @@ n = keys.shape[0]
 nbr, npairs = ops.kernel_map_k3(keys, ops.HashTable(keys), count_pairs=True)
 pairs = int(npairs.item())
 print(f"rows {n} pairs {pairs} ({pairs / n:.2f} nbrs/row)")
+if args.dump:
+    with open(args.dump, "wb") as fh:
+        fh.write(np.array([n, pairs], dtype=np.int64).tobytes())
+        fh.write(nbr.cpu().numpy().tobytes())
 g = torch.Generator().manual_seed(0)
 for shape in args.shapes.split(","):
     cin, cout = map(int, shape.split("x"))
