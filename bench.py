@@ -90,6 +90,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from pcgcv2_b200 import _lib, ops, synth
+    from pcgcv2_b200 import dist as pdist
     from pcgcv2_b200.codec import Codec
 
     torch.cuda.set_device(local_rank)
@@ -133,11 +134,7 @@ def run_ours(args, rank, world, local_rank):
             last = fn()
         end.record()
         barrier()
-        ms = start.elapsed_time(end)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = pdist.max_over_ranks(start.elapsed_time(end), dev)
         return ms, last, _lib.launch_count() - launches0, (t0, time.time())
 
     for _ in range(args.warmup):
@@ -164,19 +161,16 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop(t0, t1) if sampler else None
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)
 
-    counters = torch.tensor([n0, st.bits(), out.shape[0]], dtype=torch.int64, device=dev)
-    if world > 1:                                            # the path's only collective: per-rank counters
-        gathered = [torch.zeros_like(counters) for _ in range(world)]
-        dist.all_gather(gathered, counters)
-        counters = torch.stack(gathered).sum(0)
-    total_pts, total_bits = int(counters[0]), int(counters[1])
+    # the path's only collective: per-rank counters
+    counters = pdist.gather_counters(torch.tensor([n0, st.bits(), out.shape[0]], dtype=torch.int64, device=dev))
+    total_pts, total_bits = int(counters[:, 0].sum()), int(counters[:, 1].sum())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     ms_step = ms_total / args.steps
-    value = total_pts / (ms_step * 1e-3) / 1e6
-    e2e_value = total_pts / (ms_e2e / args.steps * 1e-3) / 1e6
+    value = pdist.aggregate_throughput(counters[:, 0], ms_step)
+    e2e_value = pdist.aggregate_throughput(counters[:, 0], ms_e2e / args.steps)
     kern_ms = float(np.mean(probe_ms))
     alg = k3_algorithmic_bytes(probe_n, probe_pairs, 16, 16)
     achieved = alg / (kern_ms * 1e-3) / 1e9
