@@ -153,6 +153,28 @@ int pcgc_conv_k2s2_fwd(const float *in, int32_t in_ld, const uint64_t *in_keys, 
 int pcgc_convT_k2s2_fwd(const float *in, int32_t in_ld, int64_t n_in, const float *weight, const float *bias,
                         int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, void *stream);
 
+/* ---- backward passes (row a16; MinkowskiEngine Convolution*Backward driven by trainer.py:136) -----
+ * Input gradients of the k=3 and k=1 convolutions are forward convolutions of grad_out with the
+ * transposed weights (offset-flipped for k=3: W'[k] = W[26-k]^T; stride-1 kernel maps are symmetric),
+ * so only the operations without a forward twin are exported here. */
+
+/* grad_weight [kvol][cin][cout] = sum over pairs of in[a]^T (x) grad_out[b]; kvol 27 with the kernel
+ * map of pcgc_kernel_map_k3, or kvol 1 with nbr == NULL (k=1 convolution). */
+int pcgc_conv_bwd_weight(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, int32_t kvol,
+                         const float *grad_out, int32_t go_ld, int32_t cin, int32_t cout,
+                         float *grad_weight, void *stream);
+/* k=2 s=2 down convolution: grad_in[u] = grad_out[parent_of[u]] @ W[key&7]^T, grad_weight [8][cin][cout]
+ * (either output may be NULL). */
+int pcgc_conv_k2s2_bwd(const float *in, int32_t in_ld, const uint64_t *in_keys, const int32_t *parent_of,
+                       int64_t n_in, const float *grad_out, int32_t go_ld, const float *weight, int32_t cin,
+                       int32_t cout, float *grad_in, int32_t gi_ld, float *grad_weight, void *stream);
+/* generative k=2 s=2 up convolution: grad_in[i] = sum_k grad_out[8i+k] @ W[k]^T, grad_weight [8][cin][cout]. */
+int pcgc_convT_k2s2_bwd(const float *in, int32_t in_ld, int64_t n_in, const float *grad_out, int32_t go_ld,
+                        const float *weight, int32_t cin, int32_t cout, float *grad_in, int32_t gi_ld,
+                        float *grad_weight, void *stream);
+/* out[c] = sum over rows of x[r][c]  (bias gradients). */
+int pcgc_colsum(const float *x, int32_t ld, int64_t n, int32_t c, float *out, void *stream);
+
 /* ---- selection / pruning (rows a8, a9) --------------------------------------------------- */
 
 /* a9  istopk -- data_utils.py:77-89 (torch.topk on the CPU in the reference): mask[i] = 1 on

@@ -54,6 +54,10 @@ SIGNATURES = {
     "pcgc_conv_k1_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),
     "pcgc_conv_k2s2_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_i32, c_p]),
     "pcgc_convT_k2s2_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_i32, c_p]),
+    "pcgc_conv_bwd_weight": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_i32, c_p, c_p]),
+    "pcgc_conv_k2s2_bwd": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_i64, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_p]),
+    "pcgc_convT_k2s2_bwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_p]),
+    "pcgc_colsum": (ctypes.c_int, [c_p, c_i32, c_i64, c_i32, c_p, c_p]),
     "pcgc_topk_mask_ws_bytes": (c_sz, [c_i64]),
     "pcgc_topk_mask": (ctypes.c_int, [c_p, c_i32, c_i64, c_i64, c_p, c_p, c_sz, c_p]),
     "pcgc_prune_ws_bytes": (c_sz, [c_i64]),

@@ -250,6 +250,47 @@ def convT_k2s2(feats, weight, bias=None, relu=False, out=None):
     return out
 
 
+# ------------------------------------------------------------------ backward passes (row a16)
+
+def conv_bwd_weight(feats, nbr, grad_out, kvol, cin, cout):
+    """grad of `kernel` for k=3 (kvol 27, nbr given) / k=1 (kvol 1, nbr None) -> [kvol, cin, cout]."""
+    feats, grad_out = _feat(feats), _feat(grad_out)
+    gw = torch.empty((kvol, cin, cout), dtype=torch.float32, device=feats.device)
+    check(_lib.lib().pcgc_conv_bwd_weight(_p(feats), feats.stride(0), _p(nbr), feats.shape[0], kvol, _p(grad_out),
+                                          grad_out.stride(0), cin, cout, _p(gw), _stream()), "pcgc_conv_bwd_weight")
+    return gw
+
+
+def conv_k2s2_bwd(feats, in_keys, parent_of, grad_out, weight, need_input_grad=True):
+    feats, grad_out = _feat(feats), _feat(grad_out)
+    n, cin = feats.shape
+    cout = weight.shape[2]
+    gi = torch.empty((n, cin), dtype=torch.float32, device=feats.device) if need_input_grad else None
+    gw = torch.empty_like(weight)
+    check(_lib.lib().pcgc_conv_k2s2_bwd(_p(feats), feats.stride(0), _p(in_keys), _p(parent_of), n, _p(grad_out),
+                                        grad_out.stride(0), _p(weight), cin, cout, _p(gi), cin, _p(gw), _stream()),
+          "pcgc_conv_k2s2_bwd")
+    return gi, gw
+
+
+def convT_k2s2_bwd(feats, grad_out, weight, need_input_grad=True):
+    feats, grad_out = _feat(feats), _feat(grad_out)
+    n, cin = feats.shape
+    cout = weight.shape[2]
+    gi = torch.empty((n, cin), dtype=torch.float32, device=feats.device) if need_input_grad else None
+    gw = torch.empty_like(weight)
+    check(_lib.lib().pcgc_convT_k2s2_bwd(_p(feats), feats.stride(0), n, _p(grad_out), grad_out.stride(0), _p(weight), cin,
+                                         cout, _p(gi), cin, _p(gw), _stream()), "pcgc_convT_k2s2_bwd")
+    return gi, gw
+
+
+def colsum(x):
+    x = _feat(x)
+    out = torch.empty((1, x.shape[1]), dtype=torch.float32, device=x.device)
+    check(_lib.lib().pcgc_colsum(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(out), _stream()), "pcgc_colsum")
+    return out
+
+
 # ------------------------------------------------------------------ selection / pruning
 
 def topk_mask(logits: torch.Tensor, k: int) -> torch.Tensor:

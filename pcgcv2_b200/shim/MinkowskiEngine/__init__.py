@@ -116,9 +116,9 @@ class CoordinateManager:
         """output map of a kernel_size=2, stride=2 convolution (Appendix A.5); cached."""
         cmap = self._get(key)
         if cmap.down is None:
-            pk, rows, off = _ops.stride_down(cmap.keys, keys_are_sorted=cmap.sorted)
+            pk, rows, off, parent_of = _ops.stride_down(cmap.keys, keys_are_sorted=cmap.sorted, with_parent_of=True)
             child = self._insert(_CoordMap(pk, cmap.stride * 2, sorted_keys=True))
-            cmap.down = (child, rows, off)
+            cmap.down = (child, rows, off, parent_of)
         return cmap.down[0]
 
     def stride_region(self, key: CoordinateMapKey) -> CoordinateMapKey:
@@ -284,11 +284,96 @@ def cat(*sparse_tensors):
     return first._like(torch.cat([t.F for t in sparse_tensors], dim=1))
 
 
-def _no_backward(*tensors):
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise NotImplementedError(
-            "pcgcv2_b200: the backward pass of the sparse convolutions is not implemented yet "
-            "(SURVEY.md section 8 row a16); run under torch.no_grad()")
+# ---- autograd: forward = libpcgc kernels; backward = libpcgc kernels -------------
+class _ConvK3Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, kernel, bias, nbr):
+        ctx.save_for_backward(feats, kernel)
+        ctx.nbr, ctx.has_bias = nbr, bias is not None
+        return _ops.conv_k3(feats, nbr, kernel, bias)
+
+    @staticmethod
+    def backward(ctx, go):
+        feats, kernel = ctx.saved_tensors
+        go = go.contiguous()
+        gi = gw = gb = None
+        if ctx.needs_input_grad[0]:      # stride-1 maps are symmetric: a forward conv with W'[k] = W[26-k]^T
+            gi = _ops.conv_k3(go, ctx.nbr, kernel.flip(0).transpose(1, 2).contiguous())
+        if ctx.needs_input_grad[1]:
+            gw = _ops.conv_bwd_weight(feats, ctx.nbr, go, 27, kernel.shape[1], kernel.shape[2])
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = _ops.colsum(go)
+        return gi, gw, gb, None
+
+
+class _ConvK1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, kernel, bias):
+        ctx.save_for_backward(feats, kernel)
+        ctx.has_bias = bias is not None
+        return _ops.conv_k1(feats, kernel, bias)
+
+    @staticmethod
+    def backward(ctx, go):
+        feats, kernel = ctx.saved_tensors
+        go = go.contiguous()
+        gi = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gi = _ops.conv_k1(go, kernel.t().contiguous())
+        if ctx.needs_input_grad[1]:
+            gw = _ops.conv_bwd_weight(feats, None, go, 1, kernel.shape[0], kernel.shape[1]).view_as(kernel)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = _ops.colsum(go)
+        return gi, gw, gb
+
+
+class _ConvDownFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, kernel, bias, keys, rows, off, parent_of):
+        ctx.save_for_backward(feats, kernel)
+        ctx.maps, ctx.has_bias = (keys, parent_of), bias is not None
+        return _ops.conv_k2s2(feats, keys, rows, off, kernel, bias)
+
+    @staticmethod
+    def backward(ctx, go):
+        feats, kernel = ctx.saved_tensors
+        keys, parent_of = ctx.maps
+        go = go.contiguous()
+        gi, gw = _ops.conv_k2s2_bwd(feats, keys, parent_of, go, kernel, need_input_grad=ctx.needs_input_grad[0])
+        gb = _ops.colsum(go) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return gi, gw, gb, None, None, None, None
+
+
+class _ConvUpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, kernel, bias):
+        ctx.save_for_backward(feats, kernel)
+        ctx.has_bias = bias is not None
+        return _ops.convT_k2s2(feats, kernel, bias)
+
+    @staticmethod
+    def backward(ctx, go):
+        feats, kernel = ctx.saved_tensors
+        go = go.contiguous()
+        gi, gw = _ops.convT_k2s2_bwd(feats, go, kernel, need_input_grad=ctx.needs_input_grad[0])
+        gb = _ops.colsum(go) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return gi, gw, gb
+
+
+class _PruneFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, mask, keys):
+        new_keys, out = _ops.prune(mask, keys, feats)
+        ctx.kept = torch.nonzero(mask, as_tuple=False).reshape(-1)
+        ctx.n = feats.shape[0]
+        ctx.mark_non_differentiable(new_keys)
+        return out, new_keys
+
+    @staticmethod
+    def backward(ctx, go, _):
+        gi = torch.zeros((ctx.n, go.shape[1]), dtype=go.dtype, device=go.device)
+        gi.index_copy_(0, ctx.kept, go.contiguous())          # backward scatters grads to the kept rows (A.9)
+        return gi, None, None
 
 
 class _ConvBase(torch.nn.Module):
@@ -335,7 +420,6 @@ class _ConvBase(torch.nn.Module):
             raise ValueError(f"input has {x.F.shape[1]} channels, the layer expects {self.in_channels}")
         if self.kernel.device != x.device:
             raise RuntimeError("module parameters and input are on different devices (call model.to(device))")
-        _no_backward(x.F, self.kernel, self.bias)
 
 
 class MinkowskiConvolution(_ConvBase):
@@ -344,14 +428,13 @@ class MinkowskiConvolution(_ConvBase):
     def forward(self, x: SparseTensor) -> SparseTensor:
         self._check(x)
         cm, cmap = x.coordinate_manager, x._cmap
-        w, b = self.kernel.detach(), None if self.bias is None else self.bias.detach()
         if self.kernel_size == 1:
-            return x._like(_ops.conv_k1(x.F, w, b))
+            return x._like(_ConvK1Fn.apply(x.F, self.kernel, self.bias))
         if self.kernel_size == 3:
-            return x._like(_ops.conv_k3(x.F, cmap.nbr, w, b))
+            return x._like(_ConvK3Fn.apply(x.F, self.kernel, self.bias, cmap.nbr))
         out_key = cm.stride(x.coordinate_map_key)
-        _, rows, off = cmap.down
-        out = _ops.conv_k2s2(x.F, cmap.keys, rows, off, w, b)
+        _, rows, off, parent_of = cmap.down
+        out = _ConvDownFn.apply(x.F, self.kernel, self.bias, cmap.keys, rows, off, parent_of)
         return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
 
 
@@ -363,8 +446,8 @@ class MinkowskiGenerativeConvolutionTranspose(_ConvBase):
         self._check(x)
         cm = x.coordinate_manager
         out_key = cm.stride_region(x.coordinate_map_key)
-        w, b = self.kernel.detach(), None if self.bias is None else self.bias.detach()
-        return SparseTensor(_ops.convT_k2s2(x.F, w, b), coordinate_map_key=out_key, coordinate_manager=cm)
+        return SparseTensor(_ConvUpFn.apply(x.F, self.kernel, self.bias), coordinate_map_key=out_key,
+                            coordinate_manager=cm)
 
 
 class MinkowskiConvolutionTranspose(MinkowskiGenerativeConvolutionTranspose):
@@ -389,8 +472,7 @@ class MinkowskiPruning(torch.nn.Module):
     def forward(self, x: SparseTensor, mask: torch.Tensor) -> SparseTensor:
         if mask.dtype != torch.bool or mask.dim() != 1 or mask.shape[0] != len(x):
             raise ValueError("mask must be a bool vector with one entry per row")
-        _no_backward(x.F)
         cmap = x._cmap
-        keys, feats = _ops.prune(mask.to(x.device), cmap.keys, x.F)
+        feats, keys = _PruneFn.apply(x.F, mask.to(x.device), cmap.keys)
         key = x.coordinate_manager._insert(_CoordMap(keys, cmap.stride, sorted_keys=cmap.sorted))
         return SparseTensor(feats, coordinate_map_key=key, coordinate_manager=x.coordinate_manager)

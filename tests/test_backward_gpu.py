@@ -1,0 +1,133 @@
+"""Backward passes of the drop-in operators against torch autograd through the CPU
+oracle (whose operators are differentiable torch ops).  Tolerance: max|d| <= 5e-5 * max|ref|."""
+import numpy as np
+import pytest
+import torch
+
+import pcgcv2_b200
+from oracle import sparse_ref as S
+from pcgcv2_b200 import ops, synth
+from util import with_batch
+
+pytestmark = pytest.mark.gpu
+TOL = 5e-5
+
+
+def _rel(got, ref):
+    return float((got.cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def _cloud(seed, n=2500, size=14, stride=1):
+    rng = np.random.default_rng(seed)
+    pts = np.unique(rng.integers(0, size, size=(n, 3)), axis=0)
+    rng.shuffle(pts)
+    return with_batch(pts * stride)
+
+
+@pytest.fixture(scope="module")
+def ME():
+    pcgcv2_b200.install_shims()
+    import MinkowskiEngine
+    return MinkowskiEngine
+
+
+def _sparse(ME, c, f, stride=1):
+    return ME.SparseTensor(features=f, coordinates=torch.from_numpy(c), tensor_stride=stride, device="cuda")
+
+
+@pytest.mark.parametrize("cin,cout,k", [(16, 16, 3), (32, 8, 3), (1, 16, 3), (4, 8, 3), (64, 64, 3), (16, 1, 3),
+                                        (32, 8, 1), (8, 16, 1), (6, 10, 3)])
+def test_conv_stride1_backward(ME, cin, cout, k):
+    c = _cloud(cin + cout)
+    g = torch.Generator().manual_seed(cin * cout + k)
+    f = torch.randn(len(c), cin, generator=g)
+    conv = ME.MinkowskiConvolution(in_channels=cin, out_channels=cout, kernel_size=k, stride=1, bias=True, dimension=3).cuda()
+    w, b = conv.kernel.detach().cpu().clone().requires_grad_(), conv.bias.detach().cpu().clone().requires_grad_()
+    fr = f.clone().requires_grad_()
+    ref = S.conv_k3(fr, c, 1, w, b) if k == 3 else S.conv_k1(fr, w, b)
+    probe = torch.randn(ref.shape, generator=g)
+    (ref * probe).sum().backward()
+    fx = f.cuda().requires_grad_()
+    out = conv(_sparse(ME, c, fx))
+    (out.F * probe.cuda()).sum().backward()
+    assert _rel(out.F.detach(), ref.detach()) < TOL
+    assert _rel(fx.grad, fr.grad) < TOL
+    assert _rel(conv.kernel.grad, w.grad) < TOL
+    assert _rel(conv.bias.grad, b.grad) < TOL
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 32), (64, 32), (6, 10)])
+def test_down_conv_backward(ME, cin, cout):
+    c = _cloud(3 + cin, n=4000, size=20)
+    g = torch.Generator().manual_seed(cin)
+    f = torch.randn(len(c), cin, generator=g)
+    conv = ME.MinkowskiConvolution(in_channels=cin, out_channels=cout, kernel_size=2, stride=2, bias=True, dimension=3).cuda()
+    w, b = conv.kernel.detach().cpu().clone().requires_grad_(), conv.bias.detach().cpu().clone().requires_grad_()
+    fr = f.clone().requires_grad_()
+    ref, ref_c = S.conv_k2s2(fr, c, 1, w, b)
+    fx = f.cuda().requires_grad_()
+    out = conv(_sparse(ME, c, fx))
+    lut = {tuple(r): i for i, r in enumerate(ref_c.tolist())}
+    perm = torch.tensor([lut[tuple(r)] for r in out.C.cpu().numpy().tolist()])
+    probe = torch.randn(ref.shape, generator=g)
+    (ref * probe).sum().backward()
+    (out.F * probe[perm].cuda()).sum().backward()
+    assert _rel(out.F.detach(), ref.detach()[perm]) < TOL
+    assert _rel(fx.grad, fr.grad) < TOL and _rel(conv.kernel.grad, w.grad) < TOL and _rel(conv.bias.grad, b.grad) < TOL
+
+
+@pytest.mark.parametrize("cin,cout", [(8, 64), (32, 16), (6, 10)])
+def test_generative_up_conv_backward(ME, cin, cout):
+    c = _cloud(9 + cin, n=900, size=10, stride=2)
+    g = torch.Generator().manual_seed(cout)
+    f = torch.randn(len(c), cin, generator=g)
+    conv = ME.MinkowskiGenerativeConvolutionTranspose(in_channels=cin, out_channels=cout, kernel_size=2, stride=2,
+                                                      bias=True, dimension=3).cuda()
+    w, b = conv.kernel.detach().cpu().clone().requires_grad_(), conv.bias.detach().cpu().clone().requires_grad_()
+    fr = f.clone().requires_grad_()
+    ref, ref_c = S.convT_k2s2(fr, c, 2, w, b)
+    fx = f.cuda().requires_grad_()
+    out = conv(_sparse(ME, c, fx, stride=2))
+    assert (out.C.cpu().numpy() == ref_c).all()
+    probe = torch.randn(ref.shape, generator=g)
+    (ref * probe).sum().backward()
+    (out.F * probe.cuda()).sum().backward()
+    assert _rel(fx.grad, fr.grad) < TOL and _rel(conv.kernel.grad, w.grad) < TOL and _rel(conv.bias.grad, b.grad) < TOL
+
+
+def test_prune_relu_cat_add_backward(ME):
+    c = _cloud(21)
+    g = torch.Generator().manual_seed(2)
+    f = torch.randn(len(c), 8, generator=g)
+    mask = torch.rand(len(c), generator=g) < 0.5
+    fx = f.cuda().requires_grad_()
+    x = _sparse(ME, c, fx)
+    y = ME.cat(ME.MinkowskiReLU()(x), x) + ME.cat(x, x)
+    out = ME.MinkowskiPruning()(y, mask.cuda())
+    probe = torch.randn(int(mask.sum()), 16, generator=g)
+    (out.F * probe.cuda()).sum().backward()
+    fr = f.clone().requires_grad_()
+    ref = (torch.cat([torch.relu(fr), fr], 1) + torch.cat([fr, fr], 1))[mask]
+    (ref * probe).sum().backward()
+    assert _rel(out.F.detach(), ref.detach()) < TOL and _rel(fx.grad, fr.grad) < TOL
+
+
+def test_inception_block_backward_through_the_model(ME):
+    """gradients of every parameter of one InceptionResNet block + a down conv, end to end."""
+    from pcgcv2_b200.model import InceptionResNet
+    from oracle import codec_ref
+    c = _cloud(33, n=3000, size=16)
+    g = torch.Generator().manual_seed(5)
+    f = torch.randn(len(c), 16, generator=g)
+    blk = InceptionResNet(16).cuda()
+    sd = {"b." + k: v.detach().cpu().clone().requires_grad_() for k, v in blk.named_parameters()}
+    fr = f.clone().requires_grad_()
+    ref = codec_ref._irn(sd, "b", fr, c, 1, codec_ref._Maps())
+    probe = torch.randn(ref.shape, generator=g)
+    (ref * probe).sum().backward()
+    fx = f.cuda().requires_grad_()
+    out = blk(_sparse(ME, c, fx))
+    (out.F * probe.cuda()).sum().backward()
+    assert _rel(out.F.detach(), ref.detach()) < TOL and _rel(fx.grad, fr.grad) < TOL
+    for k, v in blk.named_parameters():
+        assert _rel(v.grad, sd["b." + k].grad) < TOL, k

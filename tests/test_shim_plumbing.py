@@ -30,7 +30,7 @@ def test_checkpoint_loads_strictly_into_shim_model():
         PCCModel().load_state_dict({**sd, "encoder.conv0.extra": torch.zeros(1)}, strict=True)
 
 
-def test_conv_module_refuses_cpu_and_missing_backward():
+def test_conv_module_refuses_cpu_and_unsupported_kernels():
     pcgcv2_b200.install_shims()
     import MinkowskiEngine as ME
     with pytest.raises(ValueError):
