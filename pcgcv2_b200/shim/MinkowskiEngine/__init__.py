@@ -287,9 +287,11 @@ def cat(*sparse_tensors):
 # ---- autograd: forward = libpcgc kernels; backward = libpcgc kernels -------------
 class _ConvK3Fn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, kernel, bias, nbr):
+    def forward(ctx, feats, kernel, bias, nbr, packed=None):
         ctx.save_for_backward(feats, kernel)
         ctx.nbr, ctx.has_bias = nbr, bias is not None
+        if packed is not None and feats.stride(0) % 4 == 0 and feats.data_ptr() % 16 == 0:
+            return _ops.conv_k3_packed(feats, nbr, packed, bias)            # 3xTF32 tensor-core kernel
         return _ops.conv_k3(feats, nbr, kernel, bias)
 
     @staticmethod
@@ -303,7 +305,7 @@ class _ConvK3Fn(torch.autograd.Function):
             gw = _ops.conv_bwd_weight(feats, ctx.nbr, go, 27, kernel.shape[1], kernel.shape[2])
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = _ops.colsum(go)
-        return gi, gw, gb, None
+        return gi, gw, gb, None, None
 
 
 class _ConvK1Fn(torch.autograd.Function):
@@ -425,13 +427,21 @@ class _ConvBase(torch.nn.Module):
 class MinkowskiConvolution(_ConvBase):
     """k=3 s=1, k=1 s=1 and k=2 s=2 convolutions (autoencoder.py:13-48,71-134,162-234)."""
 
+    def _packed_weights(self):
+        """k=3 weights in tensor-core fragment order, re-packed whenever the parameter changes."""
+        tag = (self.kernel._version, self.kernel.data_ptr())
+        if getattr(self, "_packed_tag", None) != tag:
+            pw = _ops.PackedK3(self.kernel.detach())
+            self._packed, self._packed_tag = (pw if pw.packed is not None else None), tag
+        return self._packed
+
     def forward(self, x: SparseTensor) -> SparseTensor:
         self._check(x)
         cm, cmap = x.coordinate_manager, x._cmap
         if self.kernel_size == 1:
             return x._like(_ConvK1Fn.apply(x.F, self.kernel, self.bias))
         if self.kernel_size == 3:
-            return x._like(_ConvK3Fn.apply(x.F, self.kernel, self.bias, cmap.nbr))
+            return x._like(_ConvK3Fn.apply(x.F, self.kernel, self.bias, cmap.nbr, self._packed_weights()))
         out_key = cm.stride(x.coordinate_map_key)
         _, rows, off, parent_of = cmap.down
         out = _ConvDownFn.apply(x.F, self.kernel, self.bias, cmap.keys, rows, off, parent_of)
