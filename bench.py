@@ -86,6 +86,15 @@ def k3_algorithmic_bytes(n, pairs, cin, cout):
     return 4 * (n * cin + n * cout) + 8 * pairs + 4 * 27 * cin * cout
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full
+    capture (profiles/r01_roofline_traffic.json), per launch; None if the capture is absent."""
+    try:
+        return int(json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")))["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -191,10 +200,12 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(out.shape[0] * 3 * 4 + st.coords.size * 4 + st.coords.shape[0] * 8 * 2)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "conv_rowlane_kernel<16,16,27> (decoder.conv2, k3 16->16)",
+        "roofline": {"bound": "hbm", "kernel": "conv_k3_mma_kernel<16,16> (decoder.conv2: k=3 conv 16->16 on the "
+                                               "finest decoder set; 3xTF32 mma.sync, gather straight into fragments)",
                      "rows": probe_n, "pairs": probe_pairs, "algorithmic_bytes": alg,
                      "kernel_ms": round(kern_ms, 4), "achieved": round(achieved, 1), "peak": hbm_peak,
-                     "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None},
+                     "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
+                     "traffic": ncu_traffic_bytes()},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(1)

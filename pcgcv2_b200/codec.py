@@ -230,13 +230,14 @@ class Codec:
         nums = np.frombuffer(stream.num_points, dtype=np.int32).tolist()
         nums[-1] = int(rho * nums[-1])                                   # coder.py:107
         level0, _, _ = self.synthesis(y[order.long()].contiguous(), level3, nums)
-        out = ops.unpack_keys(level0.keys, 1)
+        out = ops.unpack_keys(level0.keys, 1)[:, 1:]
         if not to_host:
-            return out[:, 1:]
+            return out
+        out = out.contiguous()
         n = out.shape[0]                                                 # D2H through a reusable pinned buffer
         if self._pinned_out is None or self._pinned_out.shape[0] < n:
-            self._pinned_out = torch.empty((max(n, 1) * 5 // 4, 4), dtype=torch.int32, pin_memory=True)
+            self._pinned_out = torch.empty((max(n, 1) * 5 // 4, 3), dtype=torch.int32, pin_memory=True)
         host = self._pinned_out[:n]
         host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return host.numpy()[:, 1:].copy()
+        return host.numpy()                                              # view of the pinned buffer: valid until the next decode()

@@ -163,7 +163,7 @@ def test_vox10_roundtrip_properties(r3):
     # the bottleneck coordinates are exactly the occupied 8x8x8 cells of the input
     cells = np.unique(pts // 8, axis=0)
     assert (canon(st.coords) == canon(cells)).all()
-    dec = codec.decode(st)
+    dec = codec.decode(st).copy()                                                     # decode() returns a reused pinned buffer
     assert len(dec) == n0 and len(np.unique(dec, axis=0)) == n0
     dec_cells = set(map(tuple, np.unique(dec // 8, axis=0).tolist()))
     assert dec_cells <= set(map(tuple, cells.tolist()))                              # decoded voxels stay inside coded cells
