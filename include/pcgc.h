@@ -210,6 +210,10 @@ int pcgc_prune(const uint8_t *mask, int64_t n, const uint64_t *keys, const float
 /* a12 EntropyBottleneck._likelihood -- entropy_model.py:112-130.  values/lik float32 [n][c]. */
 int pcgc_eb_likelihood_fwd(const float *values, int64_t n, int32_t channels, const float *params,
                            float *likelihood, void *stream);
+/* a12 backward: grad_values [n][c] (may be NULL) and grad_params [c][48] (same packing as params; raw-parameter
+ * gradients, i.e. through softplus / tanh) from grad_likelihood [n][c].  channels must divide 256. */
+int pcgc_eb_likelihood_bwd(const float *values, int64_t n, int32_t channels, const float *params,
+                           const float *grad_likelihood, float *grad_values, float *grad_params, void *stream);
 /* a13/a14 table of compress()/decompress() -- entropy_model.py:155-171,181-189: for symbols
  * min_v..max_v: pmf = max(likelihood, 1e-9); cdf = clamp(cumsum, max=1) with a leading 0
  * -> cdf_float [c][L+1]; cdf_u16 (may be NULL) the torchac integer table (Appendix B.1). */

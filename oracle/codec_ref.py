@@ -85,7 +85,7 @@ def encoder_forward(sd, coords: np.ndarray, feats: torch.Tensor, record=None):
     return [(y, outs[2][1], 8), outs[1], outs[0]]
 
 
-def decoder_forward(sd, coords: np.ndarray, feats: torch.Tensor, nums, record=None):
+def decoder_forward(sd, coords: np.ndarray, feats: torch.Tensor, nums, record=None, ground_truths=None):
     """``autoencoder.py:251-273`` with ``training=False`` (top-k pruning only,
     ``:239-249``).  ``nums`` = [k0, k1, k2] voxels kept per scale."""
     relu = torch.relu
@@ -107,11 +107,37 @@ def decoder_forward(sd, coords: np.ndarray, feats: torch.Tensor, nums, record=No
             x = _irn(sd, f"decoder.block{lvl}.{i}", x, coords, stride, maps, record)
         cls = _conv(sd, f"decoder.conv{lvl}_cls", x, coords, stride, maps, record)
         cls_list.append((cls, coords))
-        mask = S.topk_mask(cls, nums[lvl])
+        mask = S.topk_mask(cls.detach(), nums[lvl])
+        if ground_truths is not None:                      # training=True: autoencoder.py:241-244
+            mask = mask | S.isin(coords, ground_truths[lvl])
         x, coords = S.prune(x, coords, mask)
         if record is not None:
             record[f"decoder.prune{lvl}.C"] = coords
     return cls_list, x, coords
+
+
+def train_forward(sd, coords: np.ndarray, quantize="symbols"):
+    """``PCCModel.forward(x, training=True)`` (``pcc_model.py:26-45``) + the losses of ``trainer.py:127-134``
+    (``loss.py:7-20``) with the straight-through round quantiser (deterministic); differentiable torch ops, so
+    autograd through it is the reference for the backward kernels."""
+    coords, _ = S.unique_coords(np.asarray(coords, dtype=np.int32))
+    feats = torch.ones((len(coords), 1), dtype=torch.float32)
+    y_list = encoder_forward(sd, coords, feats)
+    yF, yC, _ = y_list[0]
+    gts = [y_list[1][1], y_list[2][1], coords]
+    nums = [len(g) for g in gts]
+    params = {"matrices": [sd[f"entropy_bottleneck._matrices.{i}"] for i in range(4)],
+              "biases": [sd[f"entropy_bottleneck._biases.{i}"] for i in range(4)],
+              "factors": [sd[f"entropy_bottleneck._factors.{i}"] for i in range(4)]}
+    yq = yF + (yF.round() - yF).detach() if quantize == "symbols" else yF
+    lik = torch.clamp(entropy_ref.likelihood(params, yq), min=entropy_ref.LIKELIHOOD_BOUND)
+    cls_list, _, _ = decoder_forward(sd, yC, yq, nums, ground_truths=gts)
+    bce = 0
+    for (cls, cls_c), gt in zip(cls_list, gts):
+        target = torch.from_numpy(S.isin(cls_c, gt).astype(np.float32))
+        bce = bce + torch.nn.functional.binary_cross_entropy_with_logits(cls.squeeze(1), target) / np.log(2.0)
+    bpp = -torch.log2(lik).sum() / float(len(coords))
+    return bce + bpp, bce, bpp
 
 
 def encode(sd, coords: np.ndarray, record=None):

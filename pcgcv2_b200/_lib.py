@@ -66,6 +66,7 @@ SIGNATURES = {
     "pcgc_prune_ws_bytes": (c_sz, [c_i64]),
     "pcgc_prune": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "pcgc_eb_likelihood_fwd": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p]),
+    "pcgc_eb_likelihood_bwd": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p, c_p, c_p]),
     "pcgc_eb_cdf_table": (ctypes.c_int, [c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p]),
     "pcgc_eb_round_minmax": (ctypes.c_int, [c_p, c_i64, c_p, c_p]),
     "pcgc_eb_symbols": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_p]),

@@ -69,6 +69,125 @@ __global__ void eb_likelihood_kernel(const float *__restrict__ values, int64_t t
         lik[i] = likelihood_at(tp + (int)(i % channels) * PPC, __ldg(values + i));
 }
 
+// ---- backward of the likelihood (training path: loss.py:17-20 bits = -sum log2 p, trainer.py:131-136) -----------
+// forward of one cumulative-logit path with every intermediate kept, then its reverse sweep.
+struct EbPath {
+    float z, v0[3], h0[3], v1[3], h1[3], v2[3], h2[3], v3;
+};
+
+__device__ __forceinline__ float eb_path_fwd(const float *__restrict__ p, float z, EbPath &s) {
+    s.z = z;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        s.v0[j] = fmaf(p[M0 + j], z, p[B0 + j]);
+        s.h0[j] = s.v0[j] + p[F0 + j] * tanhf(s.v0[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float v = p[M1 + 3 * j] * s.h0[0];
+        v = fmaf(p[M1 + 3 * j + 1], s.h0[1], v);
+        v = fmaf(p[M1 + 3 * j + 2], s.h0[2], v);
+        s.v1[j] = v + p[B1 + j];
+        s.h1[j] = s.v1[j] + p[F1 + j] * tanhf(s.v1[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float v = p[M2 + 3 * j] * s.h1[0];
+        v = fmaf(p[M2 + 3 * j + 1], s.h1[1], v);
+        v = fmaf(p[M2 + 3 * j + 2], s.h1[2], v);
+        s.v2[j] = v + p[B2 + j];
+        s.h2[j] = s.v2[j] + p[F2 + j] * tanhf(s.v2[j]);
+    }
+    float v = p[M3] * s.h2[0];
+    v = fmaf(p[M3 + 1], s.h2[1], v);
+    v = fmaf(p[M3 + 2], s.h2[2], v);
+    s.v3 = v + p[B3];
+    return s.v3 + p[F3] * tanhf(s.v3);
+}
+
+// g = dLoss/d(out of this path); accumulates d/d(transformed params) into gp[44], returns dLoss/dz
+__device__ __forceinline__ float eb_path_bwd(const float *__restrict__ p, const EbPath &s, float g, float *__restrict__ gp) {
+    float t = tanhf(s.v3);
+    gp[F3] += g * t;
+    const float dv3 = g * (1.f + p[F3] * (1.f - t * t));
+    gp[B3] += dv3;
+    float dh2[3], dh1[3] = {0.f, 0.f, 0.f}, dh0[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { gp[M3 + i] += dv3 * s.h2[i]; dh2[i] = dv3 * p[M3 + i]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        t = tanhf(s.v2[j]);
+        gp[F2 + j] += dh2[j] * t;
+        const float dv = dh2[j] * (1.f + p[F2 + j] * (1.f - t * t));
+        gp[B2 + j] += dv;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { gp[M2 + 3 * j + i] += dv * s.h1[i]; dh1[i] = fmaf(dv, p[M2 + 3 * j + i], dh1[i]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        t = tanhf(s.v1[j]);
+        gp[F1 + j] += dh1[j] * t;
+        const float dv = dh1[j] * (1.f + p[F1 + j] * (1.f - t * t));
+        gp[B1 + j] += dv;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { gp[M1 + 3 * j + i] += dv * s.h0[i]; dh0[i] = fmaf(dv, p[M1 + 3 * j + i], dh0[i]); }
+    }
+    float dz = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        t = tanhf(s.v0[j]);
+        gp[F0 + j] += dh0[j] * t;
+        const float dv = dh0[j] * (1.f + p[F0 + j] * (1.f - t * t));
+        gp[B0 + j] += dv;
+        gp[M0 + j] += dv * s.z;
+        dz = fmaf(dv, p[M0 + j], dz);
+    }
+    return dz;
+}
+
+// every thread keeps to ONE channel (blockDim and the grid stride are multiples of `channels`), accumulates the 44
+// parameter gradients of that channel in registers, then block-reduces through shared memory.
+__global__ void __launch_bounds__(256)
+eb_likelihood_bwd_kernel(const float *__restrict__ values, int64_t total, int channels, const float *__restrict__ raw,
+                         const float *__restrict__ grad_lik, float *__restrict__ grad_values,
+                         float *__restrict__ grad_params) {
+    extern __shared__ float sm[];
+    float *tp = sm;                               // transformed params [channels][PPC]
+    float *acc = sm + channels * PPC;             // block accumulators [channels][PPC]
+    transform_params(raw, tp, channels);
+    for (int i = threadIdx.x; i < channels * PPC; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    const int c = threadIdx.x % channels;
+    const float *p = tp + c * PPC;
+    float gp[44];
+#pragma unroll
+    for (int i = 0; i < 44; ++i) gp[i] = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = __ldg(values + i), g = __ldg(grad_lik + i);
+        EbPath lo, up;
+        const float lower = eb_path_fwd(p, x - 0.5f, lo), upper = eb_path_fwd(p, x + 0.5f, up);
+        const float sum = lower + upper;
+        const float sg = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
+        const float su = sigmoid_f(sg * upper), sl = sigmoid_f(sg * lower);
+        const float d = su - sl, sd = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);      // d|d|/dd
+        const float gu = g * sd * su * (1.f - su) * sg, gl = -g * sd * sl * (1.f - sl) * sg;
+        const float dx = eb_path_bwd(p, up, gu, gp) + eb_path_bwd(p, lo, gl, gp);
+        if (grad_values) grad_values[i] = dx;
+    }
+#pragma unroll
+    for (int i = 0; i < 44; ++i)
+        if (gp[i] != 0.f) atomicAdd(acc + c * PPC + i, gp[i]);
+    __syncthreads();
+    // chain rule to the raw parameters: softplus' = sigmoid, tanh' = 1 - tanh^2, biases pass through
+    for (int i = threadIdx.x; i < channels * PPC; i += blockDim.x) {
+        const int o = i % PPC;
+        if (o >= 44 || acc[i] == 0.f) continue;
+        const float r = raw[i];
+        const float scale = o < B0 ? (r > 20.f ? 1.f : sigmoid_f(r)) : (o < F0 ? 1.f : 1.f - tp[i] * tp[i]);
+        atomicAdd(grad_params + i, acc[i] * scale);
+    }
+}
+
 // one block per channel: pmf over the symbol grid, sequential cumsum (double accumulator, as the
 // reference's CPU torch.cumsum), clamp, and the torchac integer table.
 __global__ void eb_cdf_table_kernel(const float *__restrict__ raw, int channels, int min_v, int L,
@@ -133,6 +252,19 @@ int pcgc_eb_likelihood_fwd(const float *values, int64_t n, int32_t channels, con
     eb_likelihood_kernel<<<grid_for(total, 256, 4), 256, sizeof(float) * channels * PPC, (cudaStream_t)stream>>>(
         values, total, channels, params, likelihood);
     return check_launch("eb_likelihood");
+}
+
+int pcgc_eb_likelihood_bwd(const float *values, int64_t n, int32_t channels, const float *params, const float *grad_likelihood,
+                           float *grad_values, float *grad_params, void *stream) {
+    PCGC_REQUIRE(n >= 0 && channels >= 1 && channels <= 64 && 256 % channels == 0,
+                 "pcgc_eb_likelihood_bwd: channels must divide 256 (got %d)", channels);
+    cudaStream_t s = (cudaStream_t)stream;
+    PCGC_CUDA(cudaMemsetAsync(grad_params, 0, sizeof(float) * channels * PPC, s));
+    if (n == 0) return PCGC_OK;
+    const int64_t total = n * channels;
+    eb_likelihood_bwd_kernel<<<grid_for(total, 256, 2), 256, sizeof(float) * 2 * channels * PPC, s>>>(
+        values, total, channels, params, grad_likelihood, grad_values, grad_params);
+    return check_launch("eb_likelihood_bwd");
 }
 
 int pcgc_eb_cdf_table(const float *params, int32_t channels, int32_t min_v, int32_t max_v, float *cdf_float,

@@ -13,6 +13,7 @@ from __future__ import annotations
 import torch
 
 import pcgcv2_b200
+from pcgcv2_b200 import ops
 
 pcgcv2_b200.install_shims()
 import MinkowskiEngine as ME  # noqa: E402
@@ -106,16 +107,75 @@ class Decoder(torch.nn.Module):
         return cls_list, out
 
 
-class EntropyBottleneckParams(torch.nn.Module):
-    """parameter holder with the reference's names (entropy_model.py:58-80) so checkpoints load strictly;
-    evaluation happens in libpcgc (ops.eb_*)."""
+class _LikelihoodFn(torch.autograd.Function):
+    """EntropyBottleneck._likelihood (entropy_model.py:112-130) and its gradient on libpcgc kernels."""
 
-    def __init__(self, channels=8, filters=(3, 3, 3)):
+    @staticmethod
+    def forward(ctx, values, *params):
+        packed = ops.pack_eb_params(params[0:4], params[4:8], params[8:12], values.device)
+        ctx.save_for_backward(values, packed)
+        return ops.eb_likelihood(values, packed)
+
+    @staticmethod
+    def backward(ctx, g):
+        values, packed = ctx.saved_tensors
+        gv, gp = ops.eb_likelihood_bwd(values, packed, g, need_values_grad=ctx.needs_input_grad[0])
+        m, b, f = ops.unpack_eb_param_grads(gp)
+        return (gv, *m, *b, *f)
+
+
+class _RoundNoGradient(torch.autograd.Function):          # entropy_model.py:9-17
+    @staticmethod
+    def forward(ctx, x):
+        return x.round()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _LowBound(torch.autograd.Function):                 # entropy_model.py:20-39
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.clamp(x, min=1e-9)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        return g * ((x >= 1e-9) | (g < 0.0)).to(g.dtype)
+
+
+class EntropyBottleneck(torch.nn.Module):
+    """Factorised-prior bottleneck with the reference's parameter names (entropy_model.py:58-80) so checkpoints
+    load strictly; likelihoods, their gradients and the codec tables are evaluated by libpcgc (ops.eb_*)."""
+
+    def __init__(self, channels=8, filters=(3, 3, 3), init_scale=8):
         super().__init__()
         f = (1,) + tuple(filters) + (1,)
-        self._matrices = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(channels, f[i + 1], f[i])) for i in range(4)])
-        self._biases = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(channels, f[i + 1], 1)) for i in range(4)])
-        self._factors = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(channels, f[i + 1], 1)) for i in range(4)])
+        scale = float(init_scale) ** (1 / (len(filters) + 1))
+        mats, biases, factors = [], [], []
+        for i in range(4):
+            init = float(torch.log(torch.expm1(torch.tensor(1.0 / scale / f[i + 1]))))
+            mats.append(torch.nn.Parameter(torch.full((channels, f[i + 1], f[i]), init)))
+            biases.append(torch.nn.Parameter(torch.rand(channels, f[i + 1], 1) - 0.5))
+            factors.append(torch.nn.Parameter(torch.zeros(channels, f[i + 1], 1)))
+        self._matrices = torch.nn.ParameterList(mats)
+        self._biases = torch.nn.ParameterList(biases)
+        self._factors = torch.nn.ParameterList(factors)
+
+    def likelihood(self, values):
+        return _LikelihoodFn.apply(values, *self._matrices, *self._biases, *self._factors)
+
+    def forward(self, inputs, quantize_mode="noise"):
+        """entropy_model.py:132-140: quantise (uniform noise / straight-through round), likelihood, lower bound."""
+        if quantize_mode == "noise":
+            outputs = inputs + (torch.rand_like(inputs) - 0.5)
+        elif quantize_mode == "symbols":
+            outputs = _RoundNoGradient.apply(inputs)
+        else:
+            outputs = inputs
+        return outputs, _LowBound.apply(self.likelihood(outputs))
 
 
 class PCCModel(torch.nn.Module):
@@ -123,7 +183,21 @@ class PCCModel(torch.nn.Module):
         super().__init__()
         self.encoder = Encoder()
         self.decoder = Decoder()
-        self.entropy_bottleneck = EntropyBottleneckParams(ENC_CHANNELS[-1])
+        self.entropy_bottleneck = EntropyBottleneck(ENC_CHANNELS[-1])
+
+    def forward(self, x, training=True, quantize_mode=None):
+        """pcc_model.py:26-45: analysis, bottleneck likelihood, synthesis with (top-k | ground truth) pruning."""
+        y_list = self.encoder(x)
+        y = y_list[0]
+        ground_truth_list = y_list[1:] + [x]
+        nums_list = [[len(c) for c in gt.decomposed_coordinates] for gt in ground_truth_list]
+        mode = quantize_mode or ("noise" if training else "symbols")
+        y_f, likelihood = self.entropy_bottleneck(y.F, quantize_mode=mode)
+        y_q = ME.SparseTensor(features=y_f, coordinate_map_key=y.coordinate_map_key,
+                              coordinate_manager=y.coordinate_manager, device=y.device)
+        out_cls_list, out = self.decoder(y_q, nums_list, ground_truth_list, training)
+        return {"out": out, "out_cls_list": out_cls_list, "prior": y_q, "likelihood": likelihood,
+                "ground_truth_list": ground_truth_list}
 
 
 def load_model(state_dict, device="cuda") -> PCCModel:

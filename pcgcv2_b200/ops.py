@@ -379,6 +379,27 @@ def eb_likelihood(values: torch.Tensor, params: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def eb_likelihood_bwd(values: torch.Tensor, params: torch.Tensor, grad_lik: torch.Tensor, need_values_grad=True):
+    """-> (grad_values [n,c] or None, grad_params [c,48] wrt the RAW packed parameters)."""
+    values, grad_lik = _feat(values).contiguous(), _feat(grad_lik).contiguous()
+    n, c = values.shape
+    gv = torch.empty_like(values) if need_values_grad else None
+    gp = torch.empty_like(params)
+    check(_lib.lib().pcgc_eb_likelihood_bwd(_p(values), n, c, _p(params), _p(grad_lik), _p(gv), _p(gp), _stream()),
+          "pcgc_eb_likelihood_bwd")
+    return gv, gp
+
+
+def unpack_eb_param_grads(gp: torch.Tensor):
+    """[C,48] packed gradient -> (matrices, biases, factors) lists shaped like the reference parameters."""
+    c = gp.shape[0]
+    cut = lambda a, b, shape: gp[:, a:b].reshape((c,) + shape)
+    m = [cut(0, 3, (3, 1)), cut(3, 12, (3, 3)), cut(12, 21, (3, 3)), cut(21, 24, (1, 3))]
+    b = [cut(24, 27, (3, 1)), cut(27, 30, (3, 1)), cut(30, 33, (3, 1)), cut(33, 34, (1, 1))]
+    f = [cut(34, 37, (3, 1)), cut(37, 40, (3, 1)), cut(40, 43, (3, 1)), cut(43, 44, (1, 1))]
+    return m, b, f
+
+
 def eb_cdf_table(params: torch.Tensor, min_v: int, max_v: int):
     """-> (cdf_float [C, L+1] float32, cdf_u16 [C, L+1] int16-bits) on the device."""
     c = params.shape[0]

@@ -131,3 +131,74 @@ def test_inception_block_backward_through_the_model(ME):
     assert _rel(out.F.detach(), ref.detach()) < TOL and _rel(fx.grad, fr.grad) < TOL
     for k, v in blk.named_parameters():
         assert _rel(v.grad, sd["b." + k].grad) < TOL, k
+
+
+@pytest.mark.parametrize("name", ["r3", "r7"])
+def test_entropy_bottleneck_likelihood_backward(name):
+    """pcgc_eb_likelihood_bwd vs autograd through the oracle (= the reference's own torch code path)."""
+    from oracle import entropy_ref
+    from pcgcv2_b200.model import EntropyBottleneck
+    from util import load_ckpt
+    sd = load_ckpt(name)
+    eb = EntropyBottleneck(8)
+    eb.load_state_dict({k[len("entropy_bottleneck."):]: v for k, v in sd.items() if k.startswith("entropy_bottleneck.")})
+    eb = eb.cuda()
+    g = torch.Generator().manual_seed(4)
+    vals = torch.randn(3001, 8, generator=g) * 3
+    probe = torch.rand(3001, 8, generator=g) + 0.1
+    ref_params = {"matrices": [p.detach().cpu().clone().requires_grad_() for p in eb._matrices],
+                  "biases": [p.detach().cpu().clone().requires_grad_() for p in eb._biases],
+                  "factors": [p.detach().cpu().clone().requires_grad_() for p in eb._factors]}
+    vr = vals.clone().requires_grad_()
+    (entropy_ref.likelihood(ref_params, vr) * probe).sum().backward()
+    vx = vals.cuda().requires_grad_()
+    (eb.likelihood(vx) * probe.cuda()).sum().backward()
+    assert _rel(vx.grad, vr.grad) < 1e-4
+    for kind, plist in (("matrices", eb._matrices), ("biases", eb._biases), ("factors", eb._factors)):
+        for i, p in enumerate(plist):
+            ref = ref_params[kind][i].grad
+            assert float((p.grad.cpu() - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-6, (kind, i)
+
+
+def test_training_step_matches_oracle_and_learns(ME):
+    """config-5 flavour: PCCModel.forward(training) + BCE/bits losses + backward on a 64^3 crop."""
+    from oracle import codec_ref
+    from pcgcv2_b200.model import load_model
+    from util import load_ckpt
+    rng = np.random.default_rng(3)
+    u = rng.normal(size=(30000, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    pts = np.unique(np.round(32 + u * np.array([20, 14, 26])).astype(np.int32), axis=0)       # ellipsoid shell in 64^3
+    coords = with_batch(pts)
+    sd = load_ckpt("r3")
+    model = load_model(sd).train()
+    x = ME.SparseTensor(features=torch.ones(len(coords), 1), coordinates=torch.from_numpy(coords), device="cuda")
+    out = model(x, training=True, quantize_mode="symbols")
+    crit = torch.nn.BCEWithLogitsLoss()
+    from data_utils import isin
+    bce = 0
+    for cls, gt in zip(out["out_cls_list"], out["ground_truth_list"]):
+        bce = bce + crit(cls.F.squeeze(), isin(cls.C, gt.C).float()) / np.log(2.0)             # loss.py:7-15, trainer.py:129
+    bpp = -torch.log2(out["likelihood"]).sum() / float(len(x))
+    loss = bce + bpp
+    loss.backward()
+    sdr = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    ref_loss, ref_bce, ref_bpp = codec_ref.train_forward(sdr, coords)
+    ref_loss.backward()
+    assert abs(float(bce) - float(ref_bce)) < 1e-3 * float(ref_bce) and abs(float(bpp) - float(ref_bpp)) < 1e-3 * float(ref_bpp) + 1e-6
+    checked = 0
+    for k, p in model.named_parameters():
+        ref = sdr[k].grad
+        if ref is None or float(ref.abs().max()) < 1e-6:
+            continue
+        assert float((p.grad.cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max()), k
+        checked += 1
+    assert checked > 150
+    # and one optimiser step lowers the loss on the same batch
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt.step()
+    with torch.no_grad():
+        out2 = model(x, training=True, quantize_mode="symbols")
+        bce2 = sum(crit(cls.F.squeeze(), isin(cls.C, gt.C).float()) / np.log(2.0)
+                   for cls, gt in zip(out2["out_cls_list"], out2["ground_truth_list"]))
+        loss2 = bce2 - torch.log2(out2["likelihood"]).sum() / float(len(x))
+    assert float(loss2) < float(loss)
