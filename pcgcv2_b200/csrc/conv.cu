@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "conv_dispatch.h"
 #include "conv_mma.cuh"
+#include "conv_pipe.cuh"
 #include "conv_tc05.cuh"
 
 namespace pcgc {
@@ -121,13 +122,21 @@ int pcgc_conv_k3_fwd(const float *in, int32_t in_ld, const int32_t *nbr, int64_t
 size_t pcgc_conv_k3_packed_floats(int32_t cin, int32_t cout) {
     const bool ok = (cin == 8 || cin == 16 || cin == 32 || cin == 64) &&
                     (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32 || cout == 64);
-    return ok ? (size_t)27 * (cin / 8) * ((cout + 15) / 16) * 256 : 0;
+    if (!ok) return 0;
+    if (pipe_route(cin, cout) == kRoutePipeNT) return (size_t)27 * (cin / 8) * ((cout + 7) / 8) * 128;
+    return (size_t)27 * (cin / 8) * ((cout + 15) / 16) * 256;
 }
 
 int pcgc_conv_k3_pack_weights(const float *weight, int32_t cin, int32_t cout, float *packed, void *stream) {
     const size_t total = pcgc_conv_k3_packed_floats(cin, cout);
     PCGC_REQUIRE(total > 0 && weight && packed, "pcgc_conv_k3_pack_weights: no tensor-core kernel for %dx%d", cin, cout);
-    pack_weights_mma_kernel<<<grid_for((int64_t)total / 2, 256, 4), 256, 0, (cudaStream_t)stream>>>(weight, 27, cin, cout, packed);
+    // the fragment layout follows the kernel that will consume it (conv_pipe.cuh: pipe_route)
+    const int grid = grid_for((int64_t)total / 2, 256, 4);
+    switch (pipe_route(cin, cout)) {
+        case kRoutePipeNT: pack_weights_nt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(weight, 27, cin, cout, packed); break;
+        case kRoutePipeT: pack_weights_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(weight, 27, cin, cout, packed); break;
+        default: pack_weights_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(weight, 27, cin, cout, packed); break;
+    }
     return check_launch("pack_weights_mma");
 }
 

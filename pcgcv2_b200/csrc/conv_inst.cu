@@ -6,6 +6,7 @@
 #include "conv_rowlane.cuh"
 #include "conv_tile.cuh"
 #include "conv_mma.cuh"
+#include "conv_pipe.cuh"
 #include "conv_dispatch.h"
 
 namespace pcgc {
@@ -135,7 +136,23 @@ static int up_case(const float *in, int in_ld, int64_t n_in, const float *w, con
 template <int CO>
 static int mma_case(const float *in, int in_ld, const int32_t *nbr, int64_t n, const float *packed, const float *b,
                     const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s) {
-    if constexpr ((CI == 8 || CI == 16 || CI == 32 || CI == 64) && CO <= 64) {
+    if constexpr ((CI == 8 || CI == 16 || CI == 32 || CI == 64) && CO <= 64 && pipe_route(CI, CO) != kRouteMma) {
+        using T = PipeTune<CI, CO>;
+        using C = PipeCfg<CI, CO, T::NT, T::RG, T::D>;
+        const size_t smem = C::smem_bytes();
+        auto kern = conv_k3_pipe_kernel<CI, CO, T::NT, T::RG, T::D, T::MINB, T::OPT>;
+        int rc = prepare_smem(kern, smem);
+        if (rc) return rc;
+        static int ctas = 0;                               // resident CTAs per SM of this instantiation
+        if (ctas == 0) {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+            ctas = nb;
+        }
+        kern<<<grid_for(n, C::ROWS_PER_CTA, ctas), C::THREADS, smem, s>>>(in, in_ld, nbr, n, packed, b, res, res_ld, out,
+                                                                         out_ld, flags);
+        return check_launch("conv_k3_pipe");
+    } else if constexpr ((CI == 8 || CI == 16 || CI == 32 || CI == 64) && CO <= 64) {
         using C = MmaCfg<CI, CO>;
         const size_t smem = C::smem_bytes();
         auto kern = conv_k3_mma_kernel<CI, CO>;

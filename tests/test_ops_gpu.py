@@ -202,7 +202,7 @@ def test_conv_k3_vs_oracle(cin, cout):
         assert (wide[:, :4] == -7).all() and (wide[:, 4 + cout:] == -7).all()
 
 
-@pytest.mark.parametrize("cin,cout", [(8, 16), (8, 8), (16, 16), (16, 4), (16, 1), (16, 32), (32, 8), (32, 32),
+@pytest.mark.parametrize("cin,cout", [(8, 16), (8, 8), (8, 1), (16, 16), (16, 4), (16, 8), (16, 1), (16, 32), (32, 8), (32, 4), (32, 32),
                                       (32, 1), (64, 16), (64, 64), (64, 1), (64, 32), (32, 64)])
 def test_conv_k3_tensor_core_vs_oracle(cin, cout):
     """3xTF32 mma.sync kernel keeps FP32 accuracy (same tolerance as the FFMA kernels)."""
