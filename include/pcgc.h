@@ -149,6 +149,19 @@ int pcgc_conv_k3_tcgen05_pack_weights(const float *weight, int32_t cin, int32_t 
 int pcgc_conv_k3_fwd_tcgen05(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, const float *packed,
                              const float *bias, int32_t cin, int32_t cout, const float *residual,
                              int32_t res_ld, float *out, int32_t out_ld, int32_t flags, void *stream);
+/* a3 on FULL-OCTET sets (every set the synthesis network convolves on is the 8-child expansion of a parent
+ * set, ME.MinkowskiGenerativeConvolutionTranspose autoencoder.py:155,182,209: n = 8 * n_parents rows, row
+ * 8*i + c = child c = cx + 2cy + 4cz of parent row i).  The 4x4x4 voxel halo of each octet is staged in shared
+ * memory (cp.async, contiguous sibling runs) and addressed by the PARENT set's kernel map parent_nbr
+ * [27][n_parents] alone -- the child-level map is not needed.  Same result as pcgc_conv_k3_fwd(_packed) on the
+ * child map.  pcgc_conv_k3_octet_packed_floats returns 0 for shapes without such a kernel (cin in {4,8,16},
+ * cout in {1,4,8,16}; cin 4: cout in {4,8}). */
+size_t pcgc_conv_k3_octet_packed_floats(int32_t cin, int32_t cout);
+int pcgc_conv_k3_octet_pack_weights(const float *weight, int32_t cin, int32_t cout, float *packed, void *stream);
+int pcgc_conv_k3_octet_fwd(const float *in, int32_t in_ld, const int32_t *parent_nbr, int64_t n_parents,
+                           const float *packed, const float *bias, int32_t cin, int32_t cout,
+                           const float *residual, int32_t res_ld, float *out, int32_t out_ld, int32_t flags,
+                           void *stream);
 /* a7  ME.MinkowskiConvolution(kernel_size=1) == F.mm(kernel) + bias. */
 int pcgc_conv_k1_fwd(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias,
                      int32_t cin, int32_t cout, const float *residual, int32_t res_ld, float *out,

@@ -48,6 +48,11 @@ class _Level:
         self.parent, self.parent_of, self.info = parent, parent_of, info      # info None + parent => full octets
         self._nbr = nbr
 
+    @property
+    def full_octets(self):
+        """this set is the 8-child expansion of ``parent`` (row 8i + c = child c of parent row i)."""
+        return self.parent is not None and self.info is None
+
     def __len__(self):
         return self.keys.shape[0]
 
@@ -63,7 +68,7 @@ class _Level:
 
 
 class Codec:
-    def __init__(self, state_dict, device="cuda", use_tensor_cores=True):
+    def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("pcgcv2_b200.Codec runs on a CUDA device only (there is no CPU path)")
@@ -80,6 +85,14 @@ class Codec:
                     pw = ops.PackedK3(v)
                     if pw.packed is not None:
                         self.packed[k[:-len(".kernel")]] = pw
+        # synthesis-side k=3 weights packed for the full-octet kernels (halo in shared memory, parent's map)
+        self.packed_octet = {}
+        if use_octet_kernels:
+            for k, v in self.w.items():
+                if k.startswith("decoder.") and k.endswith(".kernel") and v.dim() == 3 and v.shape[0] == 27:
+                    pw = ops.PackedK3Octet(v)
+                    if pw.packed is not None:
+                        self.packed_octet[k[:-len(".kernel")]] = pw
         self._pinned_out = None         # reusable pinned host buffer for the decoded coordinates
         self.record = None              # set to a dict to capture per-layer activations (parity tests)
         self.probe = {}                 # layer name -> list of (start, end) CUDA event pairs (bench.py roofline)
@@ -91,13 +104,17 @@ class Codec:
                                  None if level is None else level.stride)
 
     def _k3(self, name, x, level, relu=False, residual=None, out=None):
+        aligned = x.stride(0) % 4 == 0
+        po = self.packed_octet.get(name) if (level.full_octets and aligned) else None
+        pw = self.packed.get(name) if aligned else None
         ev = self.probe.get(name)
         if ev is not None:
-            nbr = level.nbr                                    # keep the (cached) map build outside the probe
+            nbr = level.parent.nbr if po is not None else level.nbr   # keep the (cached) map build outside the probe
             start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             start.record()
-        pw = self.packed.get(name)
-        if pw is not None and x.stride(0) % 4 == 0:
+        if po is not None:       # 8-child expansion: halo kernels addressed by the parent's map (no child map at all)
+            y = ops.conv_k3_octet(x, level.parent.nbr, po, self.w[name + ".bias"], residual=residual, relu=relu, out=out)
+        elif pw is not None:
             y = ops.conv_k3_packed(x, level.nbr, pw, self.w[name + ".bias"], residual=residual, relu=relu, out=out)
         else:
             y = ops.conv_k3(x, level.nbr, self.w[name + ".kernel"], self.w[name + ".bias"], residual=residual,

@@ -238,6 +238,35 @@ def conv_k3_tcgen05(feats, nbr, pw: PackedK3Tcgen05, bias=None, residual=None, r
     return out
 
 
+class PackedK3Octet:
+    """k=3 weights packed for the full-octet kernels (None if the shape has no such kernel)."""
+
+    def __init__(self, weight: torch.Tensor):
+        assert weight.dim() == 3 and weight.shape[0] == 27 and weight.is_contiguous()
+        self.cin, self.cout = int(weight.shape[1]), int(weight.shape[2])
+        n = int(_lib.lib().pcgc_conv_k3_octet_packed_floats(self.cin, self.cout))
+        self.packed = None
+        if n:
+            self.packed = torch.empty(n, dtype=torch.float32, device=weight.device)
+            check(_lib.lib().pcgc_conv_k3_octet_pack_weights(_p(weight), self.cin, self.cout, _p(self.packed), _stream()),
+                  "pcgc_conv_k3_octet_pack_weights")
+
+
+def conv_k3_octet(feats, parent_nbr, pw: PackedK3Octet, bias=None, residual=None, relu=False, out=None):
+    """k=3 convolution on the 8-child expansion of a parent set: feats [8P, cin] (row 8i+c = child c of
+    parent row i), parent_nbr int32 [27, P] = the PARENT set's kernel map."""
+    feats = _feat(feats)
+    n, cin = feats.shape
+    n_par = parent_nbr.shape[1]
+    assert cin == pw.cin and pw.packed is not None and n == 8 * n_par and parent_nbr.is_contiguous()
+    out = _out_slice(out, n, pw.cout, feats.device)
+    residual = None if residual is None else _feat(residual)
+    check(_lib.lib().pcgc_conv_k3_octet_fwd(_p(feats), feats.stride(0), _p(parent_nbr), n_par, _p(pw.packed), _p(bias), cin,
+                                            pw.cout, _p(residual), 0 if residual is None else residual.stride(0), _p(out),
+                                            out.stride(0), EPI_RELU if relu else 0, _stream()), "pcgc_conv_k3_octet_fwd")
+    return out
+
+
 def conv_k1(feats, weight, bias=None, residual=None, relu=False, out=None):
     feats = _feat(feats)
     n, cin = feats.shape

@@ -252,6 +252,65 @@ def test_conv_k3_tcgen05_vs_oracle(cout):
         assert _rel_err(got, torch.relu(S.conv_k3(f[:n], c[:n], 1, w, b))) < CONV_TOL
 
 
+OCTET_SHAPES = [(16, 16), (16, 8), (16, 4), (16, 1), (8, 16), (8, 8), (8, 4), (8, 1), (4, 8), (4, 4)]
+
+
+@pytest.mark.parametrize("cin,cout", OCTET_SHAPES)
+def test_conv_k3_octet_vs_oracle(cin, cout):
+    """full-octet kernels (halo staged in shared memory, addressed by the PARENT's map) == oracle k=3
+    convolution on the 8-child expansion, incl. tile tails, fused residual/ReLU and column-slice output."""
+    par = _surface()[:6007]                                       # parents at stride 2 (arbitrary order)
+    par[:, 1:] *= 2
+    pkeys, _ = ops.argsort_u64(_keys(par, 2))
+    pnbr = ops.kernel_map_k3(pkeys, ops.HashTable(pkeys))
+    ckeys = ops.upsample_keys(pkeys)                              # row 8i + c = child c of parent i
+    c = ops.unpack_keys(ckeys, 1).cpu().numpy()
+    g = torch.Generator().manual_seed(cin * 5 + cout)
+    f = torch.randn(len(c), cin, generator=g)
+    w = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    b = torch.randn(1, cout, generator=g)
+    ref = S.conv_k3(f, c, 1, w, b)
+    pw = ops.PackedK3Octet(w.to(DEV))
+    assert pw.packed is not None
+    got = ops.conv_k3_octet(f.to(DEV), pnbr, pw, b.to(DEV))
+    assert _rel_err(got, ref) < CONV_TOL
+    if cout % 4 == 0:
+        res = torch.randn(len(c), cout, generator=g)
+        wide = torch.full((len(c), cout + 8), -7.0, device=DEV)
+        ops.conv_k3_octet(f.to(DEV), pnbr, pw, b.to(DEV), residual=res.to(DEV), relu=True, out=wide[:, 4:4 + cout])
+        assert _rel_err(wide[:, 4:4 + cout], torch.relu(ref + res)) < CONV_TOL
+        assert (wide[:, :4] == -7).all() and (wide[:, 4 + cout:] == -7).all()
+        wide_in = torch.zeros((len(c), cin + 4), device=DEV)     # strided input rows (column slice of a wider tensor)
+        wide_in[:, 4:] = f.to(DEV)
+        assert _rel_err(ops.conv_k3_octet(wide_in[:, 4:], pnbr, pw, b.to(DEV)), ref) < CONV_TOL
+    for n_par in (1, 3, 31, 33, 257):                             # tile tails, fewer tiles than SMs
+        pk = pkeys[:n_par].contiguous()
+        nb = ops.kernel_map_k3(pk, ops.HashTable(pk))
+        cc = ops.unpack_keys(ops.upsample_keys(pk), 1).cpu().numpy()
+        got = ops.conv_k3_octet(f[:8 * n_par].to(DEV), nb, pw, b.to(DEV), relu=True)
+        assert _rel_err(got, torch.relu(S.conv_k3(f[:8 * n_par], cc, 1, w, b))) < CONV_TOL
+
+
+def test_conv_k3_octet_equals_child_map_kernels():
+    """same numbers as the child-map kernels on the same set (FFMA variant bit-identical)."""
+    par = _surface()[:20011]
+    par[:, 1:] *= 2
+    pkeys, _ = ops.argsort_u64(_keys(par, 2))
+    pnbr = ops.kernel_map_k3(pkeys, ops.HashTable(pkeys))
+    nbr = ops.kernel_map_k3_from_parent(pnbr, 8 * len(pkeys))
+    g = torch.Generator().manual_seed(3)
+    for cin, cout in ((4, 8), (4, 4), (16, 16), (16, 4), (8, 8)):
+        f = torch.randn(8 * len(pkeys), cin, generator=g).to(DEV)
+        w = (torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)).to(DEV)
+        b = torch.randn(1, cout, generator=g).to(DEV)
+        got = ops.conv_k3_octet(f, pnbr, ops.PackedK3Octet(w), b)
+        if cin == 4:
+            assert torch.equal(got, ops.conv_k3(f, nbr, w, b))
+        else:
+            want = ops.conv_k3_packed(f, nbr, ops.PackedK3(w), b)
+            assert float((got - want).abs().max() / want.abs().max()) < 2e-6
+
+
 def test_conv_k3_surface_and_ragged_sizes():
     c = _surface()
     keys = _keys(c)
