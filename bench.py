@@ -193,15 +193,16 @@ def run_ours(args, rank, world, local_rank):
                    "bpp_features": round(total_bits / total_pts, 5),
                    "coords_side_channel": "raw int32 hand-over (tmc3 subprocess out of scope)",
                    "l2": "per-step traffic (~8.6 GB algorithmic, >1 GB live) exceeds the 126 MB L2; no flush needed"},
-        # H2D: input voxels + (decode side) bottleneck coordinates and de-quantised features;
+        # H2D: input voxels + (decode side) bottleneck coordinates and int16 symbols;
         # D2H: decoded voxels + (encode side) bottleneck coordinates, int16 symbols and the uint16 table
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT,
-                "h2d_bytes_per_step": int(host_coords.numel() * 4 + st.coords.size * 4 + st.coords.shape[0] * 8 * 4),
+                "h2d_bytes_per_step": int(host_coords.numel() * 4 + st.coords.size * 4 + st.coords.shape[0] * 8 * 2),
                 "d2h_bytes_per_step": int(out.shape[0] * 3 * 4 + st.coords.size * 4 + st.coords.shape[0] * 8 * 2)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "conv_k3_mma_kernel<16,16> (decoder.conv2: k=3 conv 16->16 on the "
-                                               "finest decoder set; 3xTF32 mma.sync, gather straight into fragments)",
+        "roofline": {"bound": "hbm", "kernel": "conv_k3_octet_h2_kernel<16,16> (decoder.conv2: k=3 conv 16->16 on the "
+                                               "finest decoder set; pre-split f16 hi/lo features, mma.sync m16n8k16, "
+                                               "4x4x4 halo per octet staged in shared memory by cp.async)",
                      "rows": probe_n, "pairs": probe_pairs, "algorithmic_bytes": alg,
                      "kernel_ms": round(kern_ms, 4), "achieved": round(achieved, 1), "peak": hbm_peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),

@@ -162,6 +162,34 @@ int pcgc_conv_k3_octet_fwd(const float *in, int32_t in_ld, const int32_t *parent
                            const float *packed, const float *bias, int32_t cin, int32_t cout,
                            const float *residual, int32_t res_ld, float *out, int32_t out_ld, int32_t flags,
                            void *stream);
+/* a3 over PRE-SPLIT half-precision features ("h2" format; conv_h2.cuh).  An h2 tensor holds x = hi + lo with
+ * hi = f16(x), lo = f16(x - hi) (22 significand bits, 4 bytes per value like the fp32 it replaces; |x| < 65504):
+ * uint32 [n][c] with leading dimension in 4-byte units, every group of four channels stored as the 16 bytes
+ * {hi0 hi1 | hi2 hi3 | lo0 lo1 | lo2 lo3}, so that a gathered row is loaded straight into mma.sync.m16n8k16 f16
+ * fragments and the hot loop has no split arithmetic (the 3xTF32 kernels above split every row once per
+ * neighbour that gathers it).  Weights are packed once per layer after multiplication by `scale` (a power of two
+ * that keeps the lo parts normal); pass inv_scale = 1/scale to the convolution.  The convolution writes fp32
+ * (`out`, may be NULL) and/or h2 (`out_h2`, may be NULL; cout % 4 == 0) for the next k=3 layer; *overflow (may be
+ * NULL) is set to 1 when a value written in h2 leaves the f16 range, so the caller can re-run on the fp32 path.
+ * Same result as pcgc_conv_k3_fwd to ~1e-6 of max|out|.  packed_words returns 0 for shapes without a kernel
+ * (cin in {16,32,64}). */
+int pcgc_split_h2(const float *in, int32_t in_ld, int64_t n, int32_t c, uint32_t *out_h2, int32_t out_ld,
+                  int32_t *overflow, void *stream);
+int pcgc_join_h2(const uint32_t *in_h2, int32_t in_ld, int64_t n, int32_t c, float *out, int32_t out_ld, void *stream);
+size_t pcgc_conv_k3_h2_packed_words(int32_t cin, int32_t cout);
+int pcgc_conv_k3_h2_pack_weights(const float *weight, int32_t cin, int32_t cout, float scale, uint32_t *packed,
+                                 void *stream);
+int pcgc_conv_k3_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *nbr, int64_t n, const uint32_t *packed,
+                        float inv_scale, const float *bias, int32_t cin, int32_t cout, const float *residual,
+                        int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld,
+                        int32_t flags, int32_t *overflow, void *stream);
+/* a3 on FULL-OCTET sets over h2 features: the halo staging of pcgc_conv_k3_octet_fwd feeding the f16 arithmetic of
+ * pcgc_conv_k3_h2_fwd (same packed weights and scale as the latter).  cin = 16, cout in {1,4,8,16,32}. */
+int pcgc_conv_k3_octet_h2_supported(int32_t cin, int32_t cout);
+int pcgc_conv_k3_octet_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *parent_nbr, int64_t n_parents,
+                              const uint32_t *packed, float inv_scale, const float *bias, int32_t cin, int32_t cout,
+                              const float *residual, int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2,
+                              int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream);
 /* a7  ME.MinkowskiConvolution(kernel_size=1) == F.mm(kernel) + bias. */
 int pcgc_conv_k1_fwd(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias,
                      int32_t cin, int32_t cout, const float *residual, int32_t res_ld, float *out,

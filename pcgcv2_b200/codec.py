@@ -67,8 +67,17 @@ class _Level:
         return self._nbr
 
 
+class _F:
+    """one feature tensor in one or both storage formats: ``f`` = float32 [n, c]; ``h`` = the pre-split
+    half-precision copy (int32 [n, c], csrc/conv_h2.cuh) that the h2 k=3 kernels gather from."""
+    __slots__ = ("f", "h")
+
+    def __init__(self, f=None, h=None):
+        self.f, self.h = f, h
+
+
 class Codec:
-    def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True):
+    def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True, use_h2=True):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("pcgcv2_b200.Codec runs on a CUDA device only (there is no CPU path)")
@@ -93,32 +102,91 @@ class Codec:
                     pw = ops.PackedK3Octet(v)
                     if pw.packed is not None:
                         self.packed_octet[k[:-len(".kernel")]] = pw
-        self._pinned_out = None         # reusable pinned host buffer for the decoded coordinates
+        # k=3 weights split into f16 hi/lo fragments for the pre-split half-precision kernels (cin in {16,32,64})
+        self.packed_h2 = {}
+        if use_h2 and use_tensor_cores:
+            for k, v in self.w.items():
+                if k.endswith(".kernel") and v.dim() == 3 and v.shape[0] == 27:
+                    pw = ops.PackedK3H2(v)
+                    if pw.packed is not None:
+                        self.packed_h2[k[:-len(".kernel")]] = pw
+        # cout = 64 does not fit the resident-weight h2 kernel: run it as four 16-wide output slices of the same gather
+        self.packed_h2_slices = {}
+        if use_h2 and use_tensor_cores:
+            for k, v in self.w.items():
+                name = k[:-len(".kernel")]
+                if (k.endswith(".kernel") and v.dim() == 3 and v.shape[0] == 27 and name not in self.packed_h2
+                        and v.shape[2] % 16 == 0 and ops.PackedK3H2.supported(v.shape[1], 16)):
+                    self.packed_h2_slices[name] = [(ops.PackedK3H2(v[:, :, j:j + 16].contiguous()),
+                                                    self.w[name + ".bias"][:, j:j + 16]) for j in range(0, v.shape[2], 16)]
+        self._h2_on = bool(self.packed_h2)
+        self.use_octet = use_octet_kernels
+        self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)   # raised by an h2 producer: re-run in fp32
+        self.h2_fallbacks = 0
+        self._pinned = {}               # reusable pinned host staging buffers (decoded coordinates, symbols, flags)
+        self._tables = {}               # (lo, hi) -> host CDF table
+        self._dedupe_next = False
         self.record = None              # set to a dict to capture per-layer activations (parity tests)
         self.probe = {}                 # layer name -> list of (start, end) CUDA event pairs (bench.py roofline)
 
     # ---------------------------------------------------------------- layers
     def _rec(self, name, t, level=None):
         if self.record is not None:
+            if isinstance(t, _F):
+                t = t.f if t.f is not None else ops.join_h2(t.h)
             self.record[name] = (t.clone(), None if level is None else level.keys.clone(),
                                  None if level is None else level.stride)
 
-    def _k3(self, name, x, level, relu=False, residual=None, out=None):
-        aligned = x.stride(0) % 4 == 0
-        po = self.packed_octet.get(name) if (level.full_octets and aligned) else None
-        pw = self.packed.get(name) if aligned else None
+    def _h(self, x: _F):
+        """the h2 copy of x (split once, on first use, when the producer did not write it)."""
+        if x.h is None:
+            x.h = ops.split_h2(x.f, overflow=self._overflow)
+        return x.h
+
+    def _k3(self, name, x: _F, level, relu=False, residual=None, out=None, out_h=None, want_f=True, want_h=False) -> _F:
+        """one k=3 layer.  ``out`` / ``out_h``: column slices to write into (fp32 / h2); ``want_h``: the consumer is an
+        h2 kernel, so an h2 producer writes that format in its epilogue (others are split lazily by ``_h``)."""
+        aligned = x.f is None or x.f.stride(0) % 4 == 0
+        ph = self.packed_h2.get(name) if self._h2_on else None
+        oh = ph if (ph is not None and level.full_octets and self.use_octet and ops.octet_h2_supported(ph.cin, ph.cout)) else None
+        po = self.packed_octet.get(name) if (oh is None and level.full_octets and aligned and x.f is not None) else None
+        if po is not None:
+            ph = None
+        pw = self.packed.get(name) if (aligned and x.f is not None) else None
         ev = self.probe.get(name)
+        sl = self.packed_h2_slices.get(name) if (self._h2_on and po is None) else None
         if ev is not None:
-            nbr = level.parent.nbr if po is not None else level.nbr   # keep the (cached) map build outside the probe
+            nbr = level.parent.nbr if (po is not None or oh is not None) else level.nbr   # keep the (cached) map build outside the probe
+            if ph is not None:
+                self._h(x)
             start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             start.record()
-        if po is not None:       # 8-child expansion: halo kernels addressed by the parent's map (no child map at all)
-            y = ops.conv_k3_octet(x, level.parent.nbr, po, self.w[name + ".bias"], residual=residual, relu=relu, out=out)
+        y = _F()
+        if oh is not None:       # 8-child expansion + pre-split f16 features: halo of h2 rows, LDS.128 -> HMMA.16816
+            y.f, y.h = ops.conv_k3_octet_h2(self._h(x), level.parent.nbr, oh, self.w[name + ".bias"], residual=residual, relu=relu,
+                                            out=out, out_h2=out_h, want_f32=want_f, want_h2=want_h and oh.cout % 4 == 0,
+                                            overflow=self._overflow)
+        elif po is not None:     # 8-child expansion: halo kernels addressed by the parent's map (no child map at all)
+            y.f = ops.conv_k3_octet(x.f, level.parent.nbr, po, self.w[name + ".bias"], residual=residual, relu=relu, out=out)
+        elif ph is not None:     # pre-split f16 features: LDG.128 -> HMMA.16816, no split arithmetic in the loop
+            y.f, y.h = ops.conv_k3_h2(self._h(x), level.nbr, ph, self.w[name + ".bias"], residual=residual, relu=relu, out=out,
+                                      out_h2=out_h, want_f32=want_f, want_h2=want_h and ph.cout % 4 == 0,
+                                      overflow=self._overflow)
+        elif sl is not None:     # wide output: 16-channel slices through the h2 kernel
+            cout = 16 * len(sl)
+            n = len(level)
+            y.f = out if out is not None else (torch.empty((n, cout), dtype=torch.float32, device=self.device) if want_f else None)
+            y.h = out_h if out_h is not None else (torch.empty((n, cout), dtype=torch.int32, device=self.device) if want_h else None)
+            for j, (ps, bias) in enumerate(sl):
+                cs = slice(16 * j, 16 * j + 16)
+                ops.conv_k3_h2(self._h(x), level.nbr, ps, bias, residual=None if residual is None else residual[:, cs], relu=relu,
+                               out=None if y.f is None else y.f[:, cs], out_h2=None if y.h is None else y.h[:, cs],
+                               want_f32=False, overflow=self._overflow)
         elif pw is not None:
-            y = ops.conv_k3_packed(x, level.nbr, pw, self.w[name + ".bias"], residual=residual, relu=relu, out=out)
+            y.f = ops.conv_k3_packed(x.f, level.nbr, pw, self.w[name + ".bias"], residual=residual, relu=relu, out=out)
         else:
-            y = ops.conv_k3(x, level.nbr, self.w[name + ".kernel"], self.w[name + ".bias"], residual=residual,
-                            relu=relu, out=out)
+            y.f = ops.conv_k3(x.f, level.nbr, self.w[name + ".kernel"], self.w[name + ".bias"], residual=residual,
+                              relu=relu, out=out)
         if ev is not None:
             end.record()
             ev.append((start, end))
@@ -129,28 +197,47 @@ class Codec:
     def _k1(self, name, x, relu=False, residual=None, out=None):
         return ops.conv_k1(x, self.w[name + ".kernel"], self.w[name + ".bias"], residual=residual, relu=relu, out=out)
 
-    def _irn(self, prefix, x, level):
+    def _uses_h2(self, name, level):
+        """the layer will run on an h2 kernel (gather or full-octet variant)."""
+        if self._h2_on and name in self.packed_h2_slices and not (level.full_octets and name in self.packed_octet):
+            return True
+        if not (self._h2_on and name in self.packed_h2):
+            return False
+        if level.full_octets and name in self.packed_octet:
+            ph = self.packed_h2[name]
+            return self.use_octet and ops.octet_h2_supported(ph.cin, ph.cout)
+        return True
+
+    def _irn(self, prefix, x: _F, level) -> _F:
         """InceptionResNet (autoencoder.py:52-57) as 5 fused launches: the two branch outputs are
         written straight into the halves of the result with the residual added in the epilogue."""
-        c = x.shape[1]
+        c = x.f.shape[1]
         h = c // 2
-        out = torch.empty_like(x)
-        a = self._k3(prefix + ".conv0_0", x, level, relu=True)
-        self._k3(prefix + ".conv0_1", a, level, residual=x[:, :h], out=out[:, :h])
-        b = self._k1(prefix + ".conv1_0", x, relu=True)
+        out = _F(torch.empty_like(x.f))
+        a_h2 = self._uses_h2(prefix + ".conv0_1", level)             # conv0_0's output feeds an h2 kernel only
+        a = self._k3(prefix + ".conv0_0", x, level, relu=True, want_f=not a_h2 or self.record is not None, want_h=a_h2)
+        if a_h2:                                                     # this producer writes its half of the h2 copy too
+            out.h = torch.empty((x.f.shape[0], c), dtype=torch.int32, device=self.device)
+        self._k3(prefix + ".conv0_1", a, level, residual=x.f[:, :h], out=out.f[:, :h], out_h=None if out.h is None else out.h[:, :h])
+        b = _F(self._k1(prefix + ".conv1_0", x.f, relu=True))
         cc = self._k3(prefix + ".conv1_1", b, level, relu=True)
-        self._k1(prefix + ".conv1_2", cc, residual=x[:, h:], out=out[:, h:])
+        self._k1(prefix + ".conv1_2", cc.f, residual=x.f[:, h:], out=out.f[:, h:])
+        if out.h is not None:
+            ops.split_h2(out.f[:, h:], out=out.h[:, h:], overflow=self._overflow)
         self._rec(prefix, out, level)
         return out
 
     # ---------------------------------------------------------------- analysis / synthesis
-    def _sorted_input(self, coords: torch.Tensor):
-        """int32 [N,4] on the device -> level-0 coordinate set in Morton order (duplicates dropped)."""
+    def _sorted_input(self, coords: torch.Tensor, dedupe: bool):
+        """int32 [N,4] on the device -> (level-0 coordinate set in Morton order, device flag "has duplicates").
+        Duplicates are rare: the first pass only raises the flag (read together with the symbol range, no extra
+        synchronisation); ``dedupe`` drops them (``unique_consecutive`` synchronises for the output size)."""
         keys = ops.pack_keys(coords, 1)
         keys, _ = ops.argsort_u64(keys)
-        if keys.numel() > 1 and bool((keys[1:] == keys[:-1]).any()):
+        if dedupe:
             keys = torch.unique_consecutive(keys)
-        return _Level(keys, 1)
+        dup = (keys[1:] == keys[:-1]).any().to(torch.int32).reshape(1) if keys.numel() > 1 else self._overflow.new_zeros(1)
+        return _Level(keys, 1), dup
 
     def analysis(self, level0: _Level):
         """autoencoder.py:138-147 -> (y [N3,8], level3, [N2, N1, N0])."""
@@ -164,40 +251,40 @@ class Codec:
             levels.append(_Level(pk, levels[-1].stride * 2))
         for child, par in zip(levels[:-1], levels[1:]):
             child.parent = par
-        x = torch.ones((len(level0), 1), dtype=torch.float32, device=self.device)
+        x = _F(torch.ones((len(level0), 1), dtype=torch.float32, device=self.device))
         x = self._k3("encoder.conv0", x, level0, relu=True)
         level, sizes = level0, [len(level0)]
         for i in range(3):
             rows, off = down[i]
-            x = ops.conv_k2s2(x, level.keys, rows, off, self.w[f"encoder.down{i}.kernel"],
-                              self.w[f"encoder.down{i}.bias"], relu=True)
+            x = _F(ops.conv_k2s2(x.f, level.keys, rows, off, self.w[f"encoder.down{i}.kernel"],
+                                 self.w[f"encoder.down{i}.bias"], relu=True))
             level = levels[i + 1]
             self._rec(f"encoder.down{i}", x, level)
             for j in range(3):
                 x = self._irn(f"encoder.block{i}.{j}", x, level)
             sizes.append(len(level))
             x = self._k3(f"encoder.conv{i + 1}", x, level, relu=(i < 2))
-        return x, level, [sizes[2], sizes[1], sizes[0]]
+        return x.f, level, [sizes[2], sizes[1], sizes[0]]
 
     def synthesis(self, y: torch.Tensor, level: _Level, nums):
         """autoencoder.py:251-273 with training=False -> (final level, classifier logits per scale)."""
         x, cls_list = y, []
         for i in range(3):
-            x = ops.convT_k2s2(x, self.w[f"decoder.up{i}.kernel"], self.w[f"decoder.up{i}.bias"], relu=True)
+            x = _F(ops.convT_k2s2(x, self.w[f"decoder.up{i}.kernel"], self.w[f"decoder.up{i}.bias"], relu=True))
             level = _Level(ops.upsample_keys(level.keys), level.stride // 2, parent=level)    # full octets
             self._rec(f"decoder.up{i}", x, level)
-            x = self._k3(f"decoder.conv{i}", x, level, relu=True)
+            x = self._k3(f"decoder.conv{i}", x, level, relu=True, want_h=True)
             for j in range(3):
                 x = self._irn(f"decoder.block{i}.{j}", x, level)
-            cls = self._k3(f"decoder.conv{i}_cls", x, level)
+            cls = self._k3(f"decoder.conv{i}_cls", x, level).f
             cls_list.append((cls, level))
             k = min(len(level), int(nums[i]))
             mask = ops.topk_mask(cls, k)                    # exactly k rows survive: no size read-back needed
             if i < 2:                                       # the pruned set parents the next up-sampling
-                keys, x, nbr = ops.prune(mask, level.keys, x, nbr=level.nbr, n_kept_hint=k)
+                keys, x, nbr = ops.prune(mask, level.keys, x.f, nbr=level.nbr, n_kept_hint=k)
                 level = _Level(keys, level.stride, nbr=nbr)
             else:
-                keys, x = ops.prune(mask, level.keys, x, n_kept_hint=k)
+                keys, x = ops.prune(mask, level.keys, x.f, n_kept_hint=k)
                 level = _Level(keys, level.stride)
         return level, x, cls_list
 
@@ -210,38 +297,98 @@ class Codec:
         key = (c[:, 2] << 40) | (c[:, 1] << 20) | c[:, 0]
         return ops.argsort_u64(key.contiguous(), end_bit=60)[1].long()
 
-    @torch.no_grad()
+    def _h2_overflowed(self) -> bool:
+        """True when an h2 producer met a value outside the f16 range during the pass that just finished (call
+        after a synchronising read): the caller repeats the pass on the 3xTF32 kernels instead."""
+        if not self._h2_on or not int(self._overflow.item()):
+            return False
+        self._overflow.zero_()
+        self.h2_fallbacks += 1
+        return True
+
+    def _without_h2(self, fn, *args, **kw):
+        on, self._h2_on = self._h2_on, False
+        try:
+            return fn(*args, **kw)
+        finally:
+            self._h2_on = on
+
     def encode(self, coords) -> Stream:
         """coords: int32 [N,3] (or [N,4] with the batch column; batch 0 only) host array or tensor."""
-        coords = torch.as_tensor(coords, dtype=torch.int32)
-        if coords.shape[1] == 3:
-            coords = torch.cat([torch.zeros((len(coords), 1), dtype=torch.int32, device=coords.device), coords], dim=1)
-        level0 = self._sorted_input(coords.to(self.device, non_blocking=True))
+        st = self._encode(coords)
+        while not isinstance(st, Stream):                                # "dup": duplicates in the input; "h2": f16 range left
+            st = self._encode(coords, dedupe=True) if st == "dup" else self._without_h2(self._encode, coords, self._dedupe_next)
+        return st
+
+    def decode(self, stream: Stream, rho: float = 1.0, to_host: bool = True):
+        """-> decoded voxel coordinates int32 [N_out, 3] (host array, or device tensor if not to_host)."""
+        out = self._decode(stream, rho, to_host)
+        return out if out is not None else self._without_h2(self._decode, stream, rho, to_host)
+
+    def _host_table(self, lo: int, hi: int) -> np.ndarray:
+        """uint16-bit CDF table [C, L+1] of the symbol range on the host: a pure function of the model and (lo, hi),
+        computed on the device once (entropy_model.py:151-171) and kept."""
+        t = self._tables.get((lo, hi))
+        if t is None:
+            if len(self._tables) > 64:
+                self._tables.clear()
+            t = self._tables[(lo, hi)] = ops.eb_cdf_table(self.eb_params, lo, hi)[1].cpu().numpy()
+        return t
+
+    def _staging(self, name, shape, dtype):
+        """reusable pinned host buffer (grown geometrically): D2H copies are asynchronous and share one synchronise."""
+        n = int(np.prod(shape))
+        buf = self._pinned.get(name)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = self._pinned[name] = torch.empty(max(n, 1) * 5 // 4 + 16, dtype=dtype, pin_memory=True)
+        return buf[:n].view(shape)
+
+    @torch.no_grad()
+    def _encode(self, coords, dedupe=False):
+        coords = torch.as_tensor(coords, dtype=torch.int32).to(self.device, non_blocking=True)   # async from pinned host memory
+        if coords.shape[1] == 3:                                          # batch column added on the device
+            coords = torch.nn.functional.pad(coords, (1, 0))
+        self._dedupe_next = dedupe
+        level0, dup = self._sorted_input(coords, dedupe)
         y, level3, num_points = self.analysis(level0)
         c3 = ops.unpack_keys(level3.keys, 1)[:, 1:]                       # stride-8 coordinates / 8
         order = self._canonical_order(c3)
-        y, c3 = y[order].contiguous(), c3[order]
-        sym, lo, hi = ops.eb_quantize(y)
-        _, table = ops.eb_cdf_table(self.eb_params, lo, hi)
-        f_bytes = ops.rc_encode_u16(table.cpu().numpy(), sym.cpu().numpy())
+        y, c3 = y[order].contiguous(), c3[order].contiguous()
+        sym, mm = ops.eb_quantize_async(y)
+        # one synchronising read for everything the host needs: symbol range + flags, symbols, coordinates
+        flags_h = self._staging("flags", (4,), torch.int32)
+        sym_h, c3_h = self._staging("sym", tuple(sym.shape), torch.int16), self._staging("c3", tuple(c3.shape), torch.int32)
+        flags_h.copy_(torch.cat([mm, self._overflow, dup]), non_blocking=True)
+        sym_h.copy_(sym, non_blocking=True)
+        c3_h.copy_(c3, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        lo, hi, over, has_dup = flags_h.tolist()
+        if has_dup:
+            return "dup"
+        if over and self._h2_on:
+            self._overflow.zero_()
+            self.h2_fallbacks += 1
+            return "h2"
+        f_bytes = ops.rc_encode_u16(self._host_table(lo, hi), sym_h.numpy())
         h_bytes = (np.array(y.shape, dtype=np.int32).tobytes() + np.array(1, dtype=np.int8).tobytes() +
                    np.array([lo], dtype=np.float32).tobytes() + np.array([hi], dtype=np.float32).tobytes())
         return Stream(F=f_bytes, H=h_bytes, num_points=np.array(num_points, dtype=np.int32).tobytes(),
-                      coords=c3.cpu().numpy(), stats={"N": num_points, "sym_range": (lo, hi)})
+                      coords=c3_h.numpy().copy(), stats={"N": num_points, "sym_range": (lo, hi)})
 
     @torch.no_grad()
-    def decode(self, stream: Stream, rho: float = 1.0, to_host: bool = True):
-        """-> decoded voxel coordinates int32 [N_out, 3] (host array, or device tensor if not to_host)."""
+    def _decode(self, stream: Stream, rho: float = 1.0, to_host: bool = True):
         shape = np.frombuffer(stream.H[:8], dtype=np.int32)
         lo = int(np.frombuffer(stream.H[9:13], dtype=np.float32)[0])
         hi = int(np.frombuffer(stream.H[13:17], dtype=np.float32)[0])
         n3, ch = int(shape[0]), int(shape[1])
-        c3 = torch.as_tensor(stream.coords, dtype=torch.int32).to(self.device, non_blocking=True)
-        _, table = ops.eb_cdf_table(self.eb_params, lo, hi)
-        sym = ops.rc_decode_u16(table.cpu().numpy(), stream.F, n3 * ch).reshape(n3, ch)
-        c3 = c3[self._canonical_order(c3)]                               # coder.py:97-99
-        y = torch.from_numpy(sym.astype(np.float32)).to(self.device) + float(lo)
-        keys = ops.pack_keys(torch.cat([torch.zeros((n3, 1), dtype=torch.int32, device=self.device), c3 * 8], dim=1), 8)
+        c3_h = self._staging("c3_in", (n3, 3), torch.int32)
+        c3_h.copy_(torch.as_tensor(stream.coords, dtype=torch.int32))
+        c3 = c3_h.to(self.device, non_blocking=True)
+        c3 = c3[self._canonical_order(c3)]                               # coder.py:97-99 (runs while the host decodes the symbols)
+        keys = ops.pack_keys(torch.nn.functional.pad(c3 * 8, (1, 0)), 8)
+        sym_h = self._staging("sym_in", (n3, ch), torch.int16)
+        ops.rc_decode_u16(self._host_table(lo, hi), stream.F, n3 * ch, out=sym_h.numpy().reshape(-1))
+        y = sym_h.to(self.device, non_blocking=True).float() + float(lo)
         keys, order = ops.argsort_u64(keys)                              # Morton order for the synthesis network
         level3 = _Level(keys, 8)
         nums = np.frombuffer(stream.num_points, dtype=np.int32).tolist()
@@ -249,12 +396,15 @@ class Codec:
         level0, _, _ = self.synthesis(y[order.long()].contiguous(), level3, nums)
         out = ops.unpack_keys(level0.keys, 1)[:, 1:]
         if not to_host:
-            return out
+            return None if self._h2_overflowed() else out
         out = out.contiguous()
-        n = out.shape[0]                                                 # D2H through a reusable pinned buffer
-        if self._pinned_out is None or self._pinned_out.shape[0] < n:
-            self._pinned_out = torch.empty((max(n, 1) * 5 // 4, 3), dtype=torch.int32, pin_memory=True)
-        host = self._pinned_out[:n]
+        host = self._staging("out", tuple(out.shape), torch.int32)       # D2H through a reusable pinned buffer
+        flag_h = self._staging("flag_out", (1,), torch.int32)
         host.copy_(out, non_blocking=True)
+        flag_h.copy_(self._overflow, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        if self._h2_on and int(flag_h[0]):
+            self._overflow.zero_()
+            self.h2_fallbacks += 1
+            return None
         return host.numpy()                                              # view of the pinned buffer: valid until the next decode()

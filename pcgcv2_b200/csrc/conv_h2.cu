@@ -1,0 +1,206 @@
+// conv_h2.cu -- C-ABI entry points of the pre-split half-precision k=3 convolution (conv_h2.cuh) and of the
+// fp32 <-> h2 feature format conversions.
+#include <cstdlib>
+
+#include "conv_h2.cuh"
+#include "conv_octet_h2.cuh"
+
+namespace pcgc {
+
+// per-shape tuning, measured on B200 with tools/bench_h2.cu on the 1.69 M-row decoder level
+// (profiles/r01_h2_sweep.txt): RG row groups per warp, D gather stages, WARPS per CTA, MINB CTAs per SM
+template <int CIN, int COUT>
+struct H2Tune {
+    static constexpr bool NT = COUT < 16;
+    static constexpr int RG = NT ? (CIN == 32 ? 2 : 1) : (CIN == 16 && COUT == 16 ? 4 : 2);
+    static constexpr int D = NT ? (CIN == 16 ? 3 : 2) : (CIN == 64 ? 1 : 2);
+    static constexpr int WARPS = (!NT && CIN * COUT >= 1024) ? 16 : 8;
+    static constexpr int MINB = NT ? (CIN == 16 ? 4 : 2) : (WARPS == 16 ? 1 : 2);
+};
+
+template <int CIN, int COUT>
+static int launch_h2(const uint32_t *in, int in_ld, const int32_t *nbr, int64_t n, const uint32_t *packed, float inv_scale,
+                     const float *bias, const float *res, int res_ld, float *out, int out_ld, uint32_t *out_h2, int out_h2_ld,
+                     int flags, int *overflow, cudaStream_t s) {
+    using T = H2Tune<CIN, COUT>;
+    using C = H2Cfg<CIN, COUT, T::NT, T::RG, T::D, T::WARPS>;
+    static_assert(C::smem_bytes() <= 227 * 1024, "h2 kernel: shared memory budget");
+    auto kern = conv_k3_h2_kernel<CIN, COUT, T::NT, T::RG, T::D, T::WARPS, T::MINB>;
+    static int ctas = 0;
+    if (ctas == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
+        if (e != cudaSuccess) { set_error("h2 conv %dx%d: %s", CIN, COUT, cudaGetErrorString(e)); return PCGC_ERR_CUDA; }
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, C::smem_bytes()) != cudaSuccess || nb < 1) nb = 1;
+        ctas = nb;
+    }
+    kern<<<grid_for(n, C::ROWS_PER_CTA, ctas), C::THREADS, C::smem_bytes(), s>>>(in, in_ld, nbr, n, packed, inv_scale, bias, res, res_ld,
+                                                                               out, out_ld, out_h2, out_h2_ld, flags, overflow);
+    return check_launch("conv_k3_h2");
+}
+
+// full-octet variant: RG row groups per warp, WARPS per CTA (one CTA per SM; each warp owns the halos of its octets).
+// PCGC_OCTET_H2_VARIANT=1|2 selects the alternatives (tools/profile_octet_h2.py sweeps them).
+template <int CIN, int COUT, int V>
+struct OctetH2Tune {
+    static constexpr bool NT = COUT < 16;
+    // measured on B200 (tools/profile_octet_h2.py, 1.69 M-row decoder level, profiles/r01_h2_sweep.txt):
+    // 16x4 0.217 ms at RG 2 / 8 warps vs 0.250 at RG 1 / 16 warps (the loop is shared-memory bound: a bigger row group
+    // re-uses each weight LDS); 16x16 0.297 vs 0.307; 16x32 0.477 vs 0.424 (registers)
+    static constexpr bool kBig = NT || COUT == 16;                // default: the bigger row group
+    static constexpr bool kUseBig = V != 2 && ((V == 0) == kBig);
+    static constexpr int RG = NT ? (kUseBig ? 2 : 1) : (kUseBig ? 4 : 2);
+    static constexpr int WARPS = V == 2 ? 20 : (kUseBig ? 8 : 16);
+};
+
+static int octet_h2_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PCGC_OCTET_H2_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
+    }
+    return v;
+}
+
+template <int CIN, int COUT, int V>
+static int launch_octet_h2_v(const uint32_t *in, int in_ld, const int32_t *pnbr, int64_t n_par, const uint32_t *packed,
+                             float inv_scale, const float *bias, const float *res, int res_ld, float *out, int out_ld,
+                             uint32_t *out_h2, int out_h2_ld, int flags, int *overflow, cudaStream_t s) {
+    using T = OctetH2Tune<CIN, COUT, V>;
+    using C = OctetH2Cfg<CIN, COUT, T::NT, T::RG, T::WARPS>;
+    static_assert(C::smem_bytes() <= 227 * 1024, "octet h2 kernel: shared memory budget");
+    auto kern = conv_k3_octet_h2_kernel<CIN, COUT, T::NT, T::RG, T::WARPS, 1>;
+    static int ctas = 0;
+    if (ctas == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
+        if (e != cudaSuccess) { set_error("octet h2 conv %dx%d: %s", CIN, COUT, cudaGetErrorString(e)); return PCGC_ERR_CUDA; }
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, C::smem_bytes()) != cudaSuccess || nb < 1) nb = 1;
+        ctas = nb;
+    }
+    kern<<<grid_for(n_par, C::OCTETS_PER_CTA, ctas), C::THREADS, C::smem_bytes(), s>>>(in, in_ld, pnbr, n_par, packed, inv_scale, bias,
+                                                                                     res, res_ld, out, out_ld, out_h2, out_h2_ld,
+                                                                                     flags, overflow);
+    return check_launch("conv_k3_octet_h2");
+}
+
+template <int CIN, int COUT>
+static int launch_octet_h2(const uint32_t *in, int in_ld, const int32_t *pnbr, int64_t n_par, const uint32_t *packed, float inv_scale,
+                           const float *bias, const float *res, int res_ld, float *out, int out_ld, uint32_t *out_h2,
+                           int out_h2_ld, int flags, int *overflow, cudaStream_t s) {
+    switch (octet_h2_variant()) {
+        case 1: return launch_octet_h2_v<CIN, COUT, 1>(in, in_ld, pnbr, n_par, packed, inv_scale, bias, res, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
+        case 2: return launch_octet_h2_v<CIN, COUT, 2>(in, in_ld, pnbr, n_par, packed, inv_scale, bias, res, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
+        default: return launch_octet_h2_v<CIN, COUT, 0>(in, in_ld, pnbr, n_par, packed, inv_scale, bias, res, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
+    }
+}
+
+static bool octet_h2_shape(int cin, int cout) { return cin == 16 && (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32); }
+
+static bool h2_shape(int cin, int cout) {
+    if (cin == 16) return cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32;
+    if (cin == 32) return cout == 1 || cout == 4 || cout == 8 || cout == 32;
+    if (cin == 64) return cout == 1 || cout == 8 || cout == 16;
+    return false;
+}
+
+}  // namespace pcgc
+
+using namespace pcgc;
+
+extern "C" {
+
+int pcgc_split_h2(const float *in, int32_t in_ld, int64_t n, int32_t c, uint32_t *out_h2, int32_t out_ld, int32_t *overflow,
+                  void *stream) {
+    PCGC_REQUIRE(n >= 0 && c >= 4 && c % 4 == 0 && in_ld >= c && out_ld >= c, "pcgc_split_h2: bad shape n=%lld c=%d ld=%d/%d",
+                 (long long)n, c, in_ld, out_ld);
+    if (n == 0) return PCGC_OK;
+    PCGC_REQUIRE(in && out_h2, "pcgc_split_h2: null pointer");
+    const int vec_ok = (in_ld % 4 == 0) && (out_ld % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out_h2 & 15) == 0);
+    split_h2_kernel<<<grid_for(n * (c / 4), 256, 8), 256, 0, (cudaStream_t)stream>>>(in, in_ld, n, c, out_h2, out_ld, overflow, vec_ok);
+    return check_launch("split_h2");
+}
+
+int pcgc_join_h2(const uint32_t *in_h2, int32_t in_ld, int64_t n, int32_t c, float *out, int32_t out_ld, void *stream) {
+    PCGC_REQUIRE(n >= 0 && c >= 4 && c % 4 == 0 && in_ld >= c && out_ld >= c, "pcgc_join_h2: bad shape n=%lld c=%d ld=%d/%d",
+                 (long long)n, c, in_ld, out_ld);
+    if (n == 0) return PCGC_OK;
+    PCGC_REQUIRE(in_h2 && out, "pcgc_join_h2: null pointer");
+    join_h2_kernel<<<grid_for(n * (c / 4), 256, 8), 256, 0, (cudaStream_t)stream>>>(in_h2, in_ld, n, c, out, out_ld);
+    return check_launch("join_h2");
+}
+
+size_t pcgc_conv_k3_h2_packed_words(int32_t cin, int32_t cout) {
+    if (!h2_shape(cin, cout)) return 0;
+    return cout < 16 ? (size_t)27 * (cin / 16) * ((cout + 7) / 8) * 128 : (size_t)27 * (cin / 16) * (cout / 16) * 256;
+}
+
+int pcgc_conv_k3_h2_pack_weights(const float *weight, int32_t cin, int32_t cout, float scale, uint32_t *packed, void *stream) {
+    const size_t total = pcgc_conv_k3_h2_packed_words(cin, cout);
+    PCGC_REQUIRE(total > 0 && weight && packed, "pcgc_conv_k3_h2_pack_weights: no h2 kernel for %dx%d", cin, cout);
+    PCGC_REQUIRE(scale > 0.f, "pcgc_conv_k3_h2_pack_weights: scale must be positive");
+    pack_weights_h2_kernel<<<grid_for((int64_t)total / 2, 256, 4), 256, 0, (cudaStream_t)stream>>>(weight, 27, cin, cout, cout < 16 ? 1 : 0,
+                                                                                                scale, packed);
+    return check_launch("pack_weights_h2");
+}
+
+int pcgc_conv_k3_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *nbr, int64_t n, const uint32_t *packed,
+                        float inv_scale, const float *bias, int32_t cin, int32_t cout, const float *residual, int32_t res_ld,
+                        float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t flags, int32_t *overflow,
+                        void *stream) {
+    PCGC_REQUIRE(n >= 0 && cin >= 1 && cout >= 1 && in_ld >= cin, "pcgc_conv_k3_h2_fwd: bad shape n=%lld cin=%d cout=%d ld=%d",
+                 (long long)n, cin, cout, in_ld);
+    if (n == 0) return PCGC_OK;
+    PCGC_REQUIRE(in_h2 && nbr && packed && (out || out_h2), "pcgc_conv_k3_h2_fwd: null pointer");
+    PCGC_REQUIRE(pcgc_conv_k3_h2_packed_words(cin, cout) > 0, "pcgc_conv_k3_h2_fwd: no h2 kernel for %dx%d", cin, cout);
+    PCGC_REQUIRE((in_ld % 4 == 0) && (((uintptr_t)in_h2 & 15) == 0) && (((uintptr_t)packed & 15) == 0),
+                 "pcgc_conv_k3_h2_fwd: input rows must be 16-byte aligned (ld %% 4 == 0)");
+    if (cout % 2 == 0) {
+        PCGC_REQUIRE(!out || (out_ld >= cout && out_ld % 2 == 0 && ((uintptr_t)out & 7) == 0), "pcgc_conv_k3_h2_fwd: out must be 8-byte aligned");
+        PCGC_REQUIRE(!residual || (res_ld % 2 == 0 && ((uintptr_t)residual & 7) == 0), "pcgc_conv_k3_h2_fwd: residual must be 8-byte aligned");
+        PCGC_REQUIRE(!out_h2 || (cout % 4 == 0 && out_h2_ld >= cout && out_h2_ld % 4 == 0 && ((uintptr_t)out_h2 & 15) == 0),
+                     "pcgc_conv_k3_h2_fwd: h2 output needs cout %% 4 == 0 and 16-byte aligned rows");
+    } else {
+        PCGC_REQUIRE(out && !out_h2 && out_ld >= cout, "pcgc_conv_k3_h2_fwd: odd cout writes fp32 only");
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+#define H2(CI, CO) \
+    if (cin == CI && cout == CO) return launch_h2<CI, CO>(in_h2, in_ld, nbr, n, packed, inv_scale, bias, residual, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
+    H2(16, 1) H2(16, 4) H2(16, 8) H2(16, 16) H2(16, 32) H2(32, 1) H2(32, 4) H2(32, 8) H2(32, 32) H2(64, 1) H2(64, 8) H2(64, 16)
+#undef H2
+    set_error("pcgc_conv_k3_h2_fwd: shape %dx%d has no instantiation", cin, cout);
+    return PCGC_ERR_INVALID;
+}
+
+int pcgc_conv_k3_octet_h2_supported(int32_t cin, int32_t cout) { return octet_h2_shape(cin, cout) ? 1 : 0; }
+
+int pcgc_conv_k3_octet_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *parent_nbr, int64_t n_parents,
+                              const uint32_t *packed, float inv_scale, const float *bias, int32_t cin, int32_t cout,
+                              const float *residual, int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2,
+                              int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream) {
+    PCGC_REQUIRE(n_parents >= 0 && 8 * n_parents < 0x7FFFFFFF && cin >= 1 && cout >= 1 && in_ld >= cin,
+                 "pcgc_conv_k3_octet_h2_fwd: bad shape n_parents=%lld cin=%d cout=%d ld=%d", (long long)n_parents, cin, cout, in_ld);
+    if (n_parents == 0) return PCGC_OK;
+    PCGC_REQUIRE(in_h2 && parent_nbr && packed && (out || out_h2), "pcgc_conv_k3_octet_h2_fwd: null pointer");
+    PCGC_REQUIRE(octet_h2_shape(cin, cout), "pcgc_conv_k3_octet_h2_fwd: no full-octet h2 kernel for %dx%d", cin, cout);
+    PCGC_REQUIRE((in_ld % 4 == 0) && (((uintptr_t)in_h2 & 15) == 0) && (((uintptr_t)packed & 15) == 0),
+                 "pcgc_conv_k3_octet_h2_fwd: input rows must be 16-byte aligned (ld %% 4 == 0)");
+    if (cout % 2 == 0) {
+        PCGC_REQUIRE(!out || (out_ld >= cout && out_ld % 2 == 0 && ((uintptr_t)out & 7) == 0), "pcgc_conv_k3_octet_h2_fwd: out must be 8-byte aligned");
+        PCGC_REQUIRE(!residual || (res_ld % 2 == 0 && ((uintptr_t)residual & 7) == 0), "pcgc_conv_k3_octet_h2_fwd: residual must be 8-byte aligned");
+        PCGC_REQUIRE(!out_h2 || (cout % 4 == 0 && out_h2_ld >= cout && out_h2_ld % 4 == 0 && ((uintptr_t)out_h2 & 15) == 0),
+                     "pcgc_conv_k3_octet_h2_fwd: h2 output needs cout %% 4 == 0 and 16-byte aligned rows");
+    } else {
+        PCGC_REQUIRE(out && !out_h2 && out_ld >= cout, "pcgc_conv_k3_octet_h2_fwd: odd cout writes fp32 only");
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+#define OH2(CI, CO) \
+    if (cin == CI && cout == CO) return launch_octet_h2<CI, CO>(in_h2, in_ld, parent_nbr, n_parents, packed, inv_scale, bias, residual, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
+    OH2(16, 1) OH2(16, 4) OH2(16, 8) OH2(16, 16) OH2(16, 32)
+#undef OH2
+    set_error("pcgc_conv_k3_octet_h2_fwd: shape %dx%d has no instantiation", cin, cout);
+    return PCGC_ERR_INVALID;
+}
+
+}  // extern "C"

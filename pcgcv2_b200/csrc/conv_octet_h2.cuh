@@ -1,0 +1,196 @@
+// conv_octet_h2.cuh -- k=3 sparse convolution on FULL-OCTET sets over pre-split half-precision features:
+// the halo staging of conv_octet.cuh (4 x 4 x 4 voxel halo of each octet in shared memory, filled by cp.async
+// from contiguous sibling runs, addressed by the PARENT's kernel map) feeding the arithmetic of conv_h2.cuh
+// (mma.sync.m16n8k16 f16, three products per term pair, operands straight from 16-byte loads).  The halo rows
+// are h2 rows (four channels = {hi0 hi1 | hi2 hi3 | lo0 lo1 | lo2 lo3}), so an LDS.128 of a halo row IS the
+// lane's MMA fragments: the 27-offset loop is LDS.128 + HMMA only -- no split, no index loads, no predicates.
+//
+//  NT (COUT <= 8):  16 rows = the same child g of two octets are the A operand, weights the B operand;
+//  T  (COUT % 16 == 0): 8 rows = the children of one octet are the B operand, weights the A operand.
+#pragma once
+#include "conv_h2.cuh"
+#include "conv_octet.cuh"
+
+namespace pcgc {
+
+template <int CIN, int COUT, bool NT_, int RG_, int WARPS_>
+struct OctetH2Cfg {
+    static_assert(CIN == 16 || CIN == 32, "octet h2 kernel: CIN in {16, 32}");
+    static_assert(NT_ || COUT % 16 == 0, "octet h2 kernel, T formulation: COUT must be a multiple of 16");
+    static constexpr bool NT = NT_;
+    static constexpr int KS = CIN / 16;                           // k-steps = 64-byte chunks per row
+    static constexpr int CT = NT ? (COUT + 7) / 8 : COUT / 16;
+    static constexpr int RG = RG_, WARPS = WARPS_, THREADS = 32 * WARPS_;
+    static constexpr int OW = NT ? 2 * RG : RG;                   // octets per warp iteration
+    static constexpr int NR = OW;                                 // halo rows read per lane per offset
+    static constexpr int ROWB = CIN * 4;
+    static constexpr int PPR = CIN / 4;
+    static constexpr int SY = 4, SZ = 4 * SY;
+    static constexpr int HROWS = 3 * SZ + 3 * SY + 4;
+    static constexpr int HB = HROWS * ROWB;
+    static constexpr int W_OFF = KS * CT * (NT ? 128 : 256);
+    static constexpr size_t packed_words() { return (size_t)27 * W_OFF; }
+    static constexpr size_t warp_bytes() { return ((size_t)OW * HB + (size_t)27 * OW * 4 + 127) / 128 * 128; }
+    static constexpr size_t smem_bytes() { return packed_words() * 4 + (size_t)WARPS * warp_bytes(); }
+    static constexpr int OCTETS_PER_CTA = WARPS * OW;
+};
+
+template <int CIN, int COUT, bool NT, int RG, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__restrict__ pnbr, int64_t n_par,
+                        const uint32_t *__restrict__ packed, float inv_scale, const float *__restrict__ bias,
+                        const float *__restrict__ residual, int res_ld, float *__restrict__ out, int out_ld,
+                        uint32_t *__restrict__ out_h2, int out_h2_ld, int flags, int *__restrict__ overflow) {
+    using C = OctetH2Cfg<CIN, COUT, NT, RG, WARPS>;
+    constexpr int KS = C::KS, CT = C::CT, OW = C::OW, NR = C::NR, ROWB = C::ROWB, PPR = C::PPR;
+    constexpr int SY = C::SY, SZ = C::SZ, HB = C::HB, W_OFF = C::W_OFF;
+    extern __shared__ __align__(128) unsigned char smem_oh2[];
+    uint32_t *wsm = reinterpret_cast<uint32_t *>(smem_oh2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    unsigned char *halo = smem_oh2 + C::packed_words() * 4 + (size_t)warp * C::warp_bytes();
+    int32_t *sidx = reinterpret_cast<int32_t *>(halo + (size_t)OW * HB);            // [27][OW] parent rows of the neighbours
+
+    for (int i = threadIdx.x; i < 27 * W_OFF / 4; i += C::THREADS) cp_async16(wsm + 4 * i, packed + 4 * i, true);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // lane's read base: child g of an octet, 16-byte piece t of each 64-byte chunk (chunk index XOR x parity for wide rows)
+    const int cx = g & 1, cy = (g >> 1) & 1, cz = g >> 2;
+    const unsigned char *slot[KS];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) slot[s] = halo + (cx + SY * cy + SZ * cz) * ROWB + (KS >= 2 ? ((s ^ cx) * 64) : 0) + t * 16;
+
+    const int64_t n_tiles = (n_par + C::OCTETS_PER_CTA - 1) / C::OCTETS_PER_CTA;
+    const char *in_bytes = reinterpret_cast<const char *>(in);
+    const uint32_t ldb = (uint32_t)in_ld * 4u;
+    H2Epilogue epi{bias, residual, out, out_h2, res_ld, out_ld, out_h2_ld, flags, inv_scale};
+    int32_t prow[OW];                                               // parent rows for the NEXT tile (lane k: neighbour k)
+    load_parent_rows<OW>(prow, pnbr, n_par, (int64_t)blockIdx.x * C::OCTETS_PER_CTA + warp * OW, lane);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t oct0 = tile * C::OCTETS_PER_CTA + warp * OW;                // first octet of this warp
+        __syncwarp();                                                             // previous iteration's readers are done
+        store_parent_rows<OW>(sidx, prow, lane);
+        __syncwarp();
+        halo_fill<PPR, OW, HB, ROWB, SY, SZ, (KS >= 2)>(halo, sidx, in_bytes, ldb, lane);
+        load_parent_rows<OW>(prow, pnbr, n_par, (tile + gridDim.x) * C::OCTETS_PER_CTA + warp * OW, lane);
+
+        float acc[CT][RG][4], small[CT][RG][4];
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+#pragma unroll
+            for (int r = 0; r < RG; ++r)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[c][r][e] = small[c][r][e] = 0.f;
+        halo_wait(0);
+
+        uint4 xb[2][NR][KS];
+        auto load_frags = [&](int o, uint4 (&x)[NR][KS]) {
+            const int ix = o % 3, iy = (o / 3) % 3, iz = o / 9;
+            const int doff = (ix + SY * iy + SZ * iz) * ROWB;
+#pragma unroll
+            for (int j = 0; j < NR; ++j)
+#pragma unroll
+                for (int q = 0; q < KS; ++q)
+                    x[j][q] = *reinterpret_cast<const uint4 *>(slot[KS >= 2 ? (q ^ (ix & 1)) : 0] + j * HB + doff);
+        };
+        load_frags(0, xb[0]);
+#pragma unroll
+        for (int o = 0; o < 27; ++o) {
+            if ((o + 1) % 9 == 0 && o + 1 < 27) halo_wait((o + 1) / 9);           // next z-plane of the halo
+            if (o + 1 < 27) load_frags(o + 1, xb[(o + 1) & 1]);
+            uint4 (&x)[NR][KS] = xb[o & 1];
+            const uint32_t *wb = wsm + (size_t)o * W_OFF;
+            float part[CT][RG][4];
+#pragma unroll
+            for (int q = 0; q < KS; ++q) {
+                if constexpr (NT) {
+                    uint4 w[CT];
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) w[c] = *reinterpret_cast<const uint4 *>(wb + ((q * CT + c) * 32 + lane) * 4);
+#pragma unroll
+                    for (int c = 0; c < CT; ++c)
+#pragma unroll
+                        for (int r = 0; r < RG; ++r)                                                   // X_lo * W_hi
+                            mma_f16(small[c][r], x[2 * r][q].z, x[2 * r + 1][q].z, x[2 * r][q].w, x[2 * r + 1][q].w, w[c].x, w[c].y);
+#pragma unroll
+                    for (int c = 0; c < CT; ++c)
+#pragma unroll
+                        for (int r = 0; r < RG; ++r) {                                                 // X_hi * W_hi
+                            if (q == 0) mma_f16_zero(part[c][r], x[2 * r][q].x, x[2 * r + 1][q].x, x[2 * r][q].y, x[2 * r + 1][q].y, w[c].x, w[c].y);
+                            else mma_f16(part[c][r], x[2 * r][q].x, x[2 * r + 1][q].x, x[2 * r][q].y, x[2 * r + 1][q].y, w[c].x, w[c].y);
+                        }
+#pragma unroll
+                    for (int c = 0; c < CT; ++c)
+#pragma unroll
+                        for (int r = 0; r < RG; ++r)                                                   // X_hi * W_lo
+                            mma_f16(small[c][r], x[2 * r][q].x, x[2 * r + 1][q].x, x[2 * r][q].y, x[2 * r + 1][q].y, w[c].z, w[c].w);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) {
+                        const uint4 *wp = reinterpret_cast<const uint4 *>(wb + (q * CT + c) * 256) + lane;
+                        const uint4 wh = wp[0], wl = wp[32];
+#pragma unroll
+                        for (int r = 0; r < RG; ++r) mma_f16(small[c][r], wh.x, wh.y, wh.z, wh.w, x[r][q].z, x[r][q].w);      // W_hi * X_lo
+#pragma unroll
+                        for (int r = 0; r < RG; ++r) {                                                                     // W_hi * X_hi
+                            if (q == 0) mma_f16_zero(part[c][r], wh.x, wh.y, wh.z, wh.w, x[r][q].x, x[r][q].y);
+                            else mma_f16(part[c][r], wh.x, wh.y, wh.z, wh.w, x[r][q].x, x[r][q].y);
+                        }
+#pragma unroll
+                        for (int r = 0; r < RG; ++r) mma_f16(small[c][r], wl.x, wl.y, wl.z, wl.w, x[r][q].x, x[r][q].y);      // W_lo * X_hi
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+#pragma unroll
+                for (int r = 0; r < RG; ++r)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[c][r][e] += part[c][r][e];
+        }
+
+        // ---- epilogue (as conv_h2.cuh)
+        const int64_t n = n_par * 8, row0 = oct0 * 8;
+        if constexpr (NT) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const int co = 8 * c + 2 * t;
+                if (co >= COUT) continue;
+#pragma unroll
+                for (int r = 0; r < RG; ++r)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int64_t row = row0 + 16 * r + 8 * h + g;
+                        if (row >= n) continue;
+                        const float v0 = acc[c][r][2 * h] + small[c][r][2 * h], v1 = acc[c][r][2 * h + 1] + small[c][r][2 * h + 1];
+                        if constexpr (COUT % 2 == 0) epi.store_pair(row, co, v0, v1);
+                        else {
+                            epi.store_one(row, co, v0);
+                            if (co + 1 < COUT) epi.store_one(row, co + 1, v1);
+                        }
+                    }
+            }
+        } else {
+            const bool odd = g & 1;
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+#pragma unroll
+                for (int r = 0; r < RG; ++r) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = acc[c][r][e] + small[c][r][e];
+                    const float r0 = __shfl_xor_sync(0xffffffffu, odd ? v[0] : v[1], 4);
+                    const float r1 = __shfl_xor_sync(0xffffffffu, odd ? v[2] : v[3], 4);
+                    const int64_t row = row0 + 8 * r + 2 * t + (odd ? 1 : 0);
+                    if (row >= n) continue;
+                    const int co = 16 * c + (g & ~1);
+                    epi.store_pair(row, co, odd ? r0 : v[0], odd ? v[1] : r0);
+                    epi.store_pair(row, co + 8, odd ? r1 : v[2], odd ? v[3] : r1);
+                }
+        }
+    }
+    if (epi.over && overflow) *overflow = 1;
+}
+
+}  // namespace pcgc

@@ -267,6 +267,101 @@ def conv_k3_octet(feats, parent_nbr, pw: PackedK3Octet, bias=None, residual=None
     return out
 
 
+# ---- pre-split half-precision ("h2") features: see include/pcgc.h and csrc/conv_h2.cuh
+def _h2(t):
+    _need_cuda(t)
+    if t.dtype != torch.int32 or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("h2 features are int32 [n, c] tensors with unit column stride")
+    return t
+
+
+def split_h2(feats, out=None, overflow=None):
+    """fp32 [n, c] -> h2 int32 [n, c] (x = f16 hi + f16 lo, 16-byte groups of four channels)."""
+    feats = _feat(feats)
+    n, c = feats.shape
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.int32, device=feats.device)
+    assert out.shape == feats.shape and out.dtype == torch.int32 and out.stride(1) == 1
+    check(_lib.lib().pcgc_split_h2(_p(feats), feats.stride(0), n, c, _p(out), out.stride(0), _p(overflow), _stream()), "pcgc_split_h2")
+    return out
+
+
+def join_h2(h2, out=None):
+    h2 = _h2(h2)
+    n, c = h2.shape
+    out = _out_slice(out, n, c, h2.device)
+    check(_lib.lib().pcgc_join_h2(_p(h2), h2.stride(0), n, c, _p(out), out.stride(0), _stream()), "pcgc_join_h2")
+    return out
+
+
+class PackedK3H2:
+    """k=3 weights split into f16 hi/lo MMA fragments after a power-of-two scale (None: no h2 kernel for the shape)."""
+
+    @staticmethod
+    def supported(cin, cout) -> bool:
+        return int(_lib.lib().pcgc_conv_k3_h2_packed_words(int(cin), int(cout))) > 0
+
+    def __init__(self, weight: torch.Tensor):
+        assert weight.dim() == 3 and weight.shape[0] == 27 and weight.is_contiguous()
+        self.cin, self.cout = int(weight.shape[1]), int(weight.shape[2])
+        n = int(_lib.lib().pcgc_conv_k3_h2_packed_words(self.cin, self.cout))
+        self.packed = None
+        if n:
+            wmax = float(weight.abs().max())
+            k = int(np.floor(np.log2(16384.0 / wmax))) if wmax > 0 and np.isfinite(wmax) else 0
+            k = max(-24, min(24, k))
+            self.scale, self.inv_scale = float(2.0 ** k), float(2.0 ** -k)
+            self.packed = torch.empty(n, dtype=torch.int32, device=weight.device)
+            check(_lib.lib().pcgc_conv_k3_h2_pack_weights(_p(weight), self.cin, self.cout, self.scale, _p(self.packed), _stream()),
+                  "pcgc_conv_k3_h2_pack_weights")
+
+
+def conv_k3_h2(feats_h2, nbr, pw: PackedK3H2, bias=None, residual=None, relu=False, out=None, out_h2=None, want_f32=True,
+               want_h2=False, overflow=None):
+    """k=3 convolution over h2 features -> (fp32 out or None, h2 out or None)."""
+    x = _h2(feats_h2)
+    n, cin = x.shape
+    assert cin == pw.cin and pw.packed is not None and nbr.shape[0] == 27 and nbr.shape[1] == n and nbr.is_contiguous()
+    if want_f32 or out is not None:
+        out = _out_slice(out, n, pw.cout, x.device)
+    if want_h2 and out_h2 is None:
+        out_h2 = torch.empty((n, pw.cout), dtype=torch.int32, device=x.device)
+    if out_h2 is not None:
+        assert out_h2.shape[0] == n and out_h2.shape[1] == pw.cout and out_h2.dtype == torch.int32 and out_h2.stride(1) == 1
+    residual = None if residual is None else _feat(residual)
+    check(_lib.lib().pcgc_conv_k3_h2_fwd(_p(x), x.stride(0), _p(nbr), n, _p(pw.packed), pw.inv_scale, _p(bias), cin, pw.cout,
+                                         _p(residual), 0 if residual is None else residual.stride(0), _p(out),
+                                         0 if out is None else out.stride(0), _p(out_h2), 0 if out_h2 is None else out_h2.stride(0),
+                                         EPI_RELU if relu else 0, _p(overflow), _stream()), "pcgc_conv_k3_h2_fwd")
+    return out, out_h2
+
+
+def octet_h2_supported(cin, cout) -> bool:
+    return bool(_lib.lib().pcgc_conv_k3_octet_h2_supported(int(cin), int(cout)))
+
+
+def conv_k3_octet_h2(feats_h2, parent_nbr, pw: PackedK3H2, bias=None, residual=None, relu=False, out=None, out_h2=None,
+                     want_f32=True, want_h2=False, overflow=None):
+    """k=3 convolution over h2 features on the 8-child expansion of a parent set (parent_nbr int32 [27, P])."""
+    x = _h2(feats_h2)
+    n, cin = x.shape
+    n_par = parent_nbr.shape[1]
+    assert cin == pw.cin and pw.packed is not None and n == 8 * n_par and parent_nbr.is_contiguous()
+    if want_f32 or out is not None:
+        out = _out_slice(out, n, pw.cout, x.device)
+    if want_h2 and out_h2 is None:
+        out_h2 = torch.empty((n, pw.cout), dtype=torch.int32, device=x.device)
+    if out_h2 is not None:
+        assert out_h2.shape[0] == n and out_h2.shape[1] == pw.cout and out_h2.dtype == torch.int32 and out_h2.stride(1) == 1
+    residual = None if residual is None else _feat(residual)
+    check(_lib.lib().pcgc_conv_k3_octet_h2_fwd(_p(x), x.stride(0), _p(parent_nbr), n_par, _p(pw.packed), pw.inv_scale, _p(bias), cin,
+                                               pw.cout, _p(residual), 0 if residual is None else residual.stride(0), _p(out),
+                                               0 if out is None else out.stride(0), _p(out_h2),
+                                               0 if out_h2 is None else out_h2.stride(0), EPI_RELU if relu else 0, _p(overflow),
+                                               _stream()), "pcgc_conv_k3_octet_h2_fwd")
+    return out, out_h2
+
+
 def conv_k1(feats, weight, bias=None, residual=None, relu=False, out=None):
     feats = _feat(feats)
     n, cin = feats.shape
@@ -440,15 +535,22 @@ def eb_cdf_table(params: torch.Tensor, min_v: int, max_v: int):
     return cdf, u16
 
 
-def eb_quantize(feats: torch.Tensor):
-    """round -> (symbols int16 [N,C] on device, min, max); one sync for min/max."""
+def eb_quantize_async(feats: torch.Tensor):
+    """round -> (symbols int16 [N,C], minmax int32 [2]) on the device, no synchronisation."""
     feats = _feat(feats).contiguous()
     count = feats.numel()
-    mm = torch.tensor([2 ** 31 - 1, -2 ** 31], dtype=torch.int32, device=feats.device)
+    mm = torch.empty(2, dtype=torch.int32, device=feats.device)
+    mm[0], mm[1] = 2 ** 31 - 1, -2 ** 31
     L = _lib.lib()
     check(L.pcgc_eb_round_minmax(_p(feats), count, _p(mm), _stream()), "pcgc_eb_round_minmax")
     sym = torch.empty(feats.shape, dtype=torch.int16, device=feats.device)
     check(L.pcgc_eb_symbols(_p(feats), count, _p(mm), _p(sym), _stream()), "pcgc_eb_symbols")
+    return sym, mm
+
+
+def eb_quantize(feats: torch.Tensor):
+    """round -> (symbols int16 [N,C] on device, min, max); one sync for min/max."""
+    sym, mm = eb_quantize_async(feats)
     lo, hi = mm.tolist()
     return sym, lo, hi
 
@@ -494,11 +596,13 @@ def rc_encode_u16(table: np.ndarray, sym: np.ndarray) -> bytes:
     return out[:n].tobytes()
 
 
-def rc_decode_u16(table: np.ndarray, data: bytes, n_sym: int) -> np.ndarray:
+def rc_decode_u16(table: np.ndarray, data: bytes, n_sym: int, out: np.ndarray | None = None) -> np.ndarray:
     table = np.ascontiguousarray(table).view(np.uint16)
     T, lp = table.shape
     buf = np.frombuffer(data, dtype=np.uint8)
-    out = np.empty(n_sym, dtype=np.int16)
+    if out is None:
+        out = np.empty(n_sym, dtype=np.int16)
+    assert out.dtype == np.int16 and out.size == n_sym and out.flags.c_contiguous
     check(_lib.lib().pcgc_rc_decode_u16_host(table.ctypes.data, T, lp, buf.ctypes.data if buf.size else None, buf.size,
                                              out.ctypes.data, n_sym), "pcgc_rc_decode_u16_host")
     return out

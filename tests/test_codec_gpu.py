@@ -172,3 +172,23 @@ def test_vox10_roundtrip_properties(r3):
     bpp = st.bits() / n0
     assert 0.03 < bpp < 0.12                                                         # r3 operating point (~0.07 bpp features)
     assert metrics_ref.d1_psnr(pts, dec, 1024) > 68.0
+
+
+def test_h2_path_equals_tf32_path_and_falls_back_on_overflow(r3):
+    """the pre-split half-precision kernels give the 3xTF32 pipeline's bitstream and occupancy; activations beyond
+    the f16 range make the codec repeat the pass on the 3xTF32 kernels instead of returning a wrong result."""
+    pts = synth.ellipsoid_vox8()
+    fast, slow = Codec(r3), Codec(r3, use_h2=False)
+    assert fast.packed_h2 and not slow.packed_h2
+    a, b = fast.encode(pts), slow.encode(pts)
+    assert a.F == b.F and a.H == b.H and (a.coords == b.coords).all()
+    assert (canon(fast.decode(a)) == canon(slow.decode(b))).all() and fast.h2_fallbacks == 0
+    fast._overflow.fill_(1)                                       # encoder side: a raised flag repeats the pass without h2
+    a2 = fast.encode(pts)
+    assert fast.h2_fallbacks == 1 and a2.F == b.F and (a2.coords == b.coords).all()
+    big = dict(r3)                                                # same bitstream, synthesis activations scaled beyond f16
+    big["decoder.up1.kernel"] = r3["decoder.up1.kernel"] * 32768.0
+    big["decoder.up1.bias"] = r3["decoder.up1.bias"] * 32768.0
+    fast, slow = Codec(big), Codec(big, use_h2=False)
+    got, want = fast.decode(a), slow.decode(b)
+    assert fast.h2_fallbacks >= 1 and (canon(got) == canon(want)).all()

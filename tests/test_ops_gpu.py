@@ -311,6 +311,130 @@ def test_conv_k3_octet_equals_child_map_kernels():
             assert float((got - want).abs().max() / want.abs().max()) < 2e-6
 
 
+H2_SHAPES = [(16, 1), (16, 4), (16, 8), (16, 16), (16, 32), (32, 1), (32, 4), (32, 8), (32, 32), (64, 1), (64, 8), (64, 16)]
+H2_TOL = 3e-6                                                     # 22-bit operands: two orders below CONV_TOL
+
+
+def test_h2_split_join_roundtrip():
+    """x -> (f16 hi, f16 lo) -> x: 22 significand bits, column slices, the overflow flag."""
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(1003, 32, generator=g) * torch.logspace(-3, 3, 32)).to(DEV)
+    h = ops.split_h2(x)
+    assert h.dtype == torch.int32 and h.shape == x.shape
+    back = ops.join_h2(h)
+    assert bool(((back - x).abs() <= torch.maximum(x.abs() * 2.0 ** -21, torch.tensor(6.0e-8, device=DEV))).all())   # lo is f16: 6e-8 quantum
+    wide = torch.zeros((1003, 48), dtype=torch.int32, device=DEV)          # a column slice of a wider h2 tensor
+    ops.split_h2(x[:, 8:24], out=wide[:, 12:28])
+    assert torch.equal(ops.join_h2(wide[:, 12:28]), back[:, 8:24]) and (wide[:, :12] == 0).all() and (wide[:, 28:] == 0).all()
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.split_h2(x, overflow=flag)
+    assert int(flag.item()) == 0
+    x[17, 5] = 7.0e4
+    ops.split_h2(x, overflow=flag)
+    assert int(flag.item()) == 1
+
+
+@pytest.mark.parametrize("cin,cout", H2_SHAPES)
+def test_conv_k3_h2_vs_oracle(cin, cout):
+    """pre-split half-precision k=3 convolution == oracle, through both outputs (fp32 and h2), with the fused
+    residual / ReLU, column-slice outputs and ragged tile tails."""
+    c = _surface()[:20011]
+    keys = _keys(c)
+    nbr = ops.kernel_map_k3(keys, ops.HashTable(keys))
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    f = torch.randn(len(c), cin, generator=g) * 3.0
+    w = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    b = torch.randn(1, cout, generator=g)
+    ref = S.conv_k3(f, c, 1, w, b)
+    pw = ops.PackedK3H2(w.to(DEV))
+    assert pw.packed is not None
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    xh = ops.split_h2(f.to(DEV))
+    got, got_h = ops.conv_k3_h2(xh, nbr, pw, b.to(DEV), want_h2=cout % 4 == 0, overflow=flag)
+    assert _rel_err(got, ref) < H2_TOL
+    if cout % 4 == 0:
+        assert _rel_err(ops.join_h2(got_h), ref) < H2_TOL
+        only_h = ops.conv_k3_h2(xh, nbr, pw, b.to(DEV), want_f32=False, want_h2=True)
+        assert only_h[0] is None and torch.equal(only_h[1], got_h)
+        res = torch.randn(len(c), cout, generator=g)
+        wide = torch.full((len(c), cout + 8), -7.0, device=DEV)
+        wide_h = torch.full((len(c), cout + 8), 5, dtype=torch.int32, device=DEV)
+        ops.conv_k3_h2(xh, nbr, pw, b.to(DEV), residual=res.to(DEV), relu=True, out=wide[:, 4:4 + cout], out_h2=wide_h[:, 4:4 + cout])
+        want = torch.relu(ref + res)
+        assert _rel_err(wide[:, 4:4 + cout], want) < H2_TOL and _rel_err(ops.join_h2(wide_h[:, 4:4 + cout]), want) < H2_TOL
+        assert (wide[:, :4] == -7).all() and (wide[:, 4 + cout:] == -7).all()
+        assert (wide_h[:, :4] == 5).all() and (wide_h[:, 4 + cout:] == 5).all()
+        wide_in = torch.zeros((len(c), cin + 4), dtype=torch.int32, device=DEV)      # strided input rows
+        wide_in[:, 4:] = xh
+        assert _rel_err(ops.conv_k3_h2(wide_in[:, 4:], nbr, pw, b.to(DEV))[0], ref) < H2_TOL
+    assert int(flag.item()) == 0
+    for n in (1, 63, 65, 2049):                                   # tile tails, fewer tiles than SMs
+        cc = c[:n]
+        kk = _keys(cc)
+        nb = ops.kernel_map_k3(kk, ops.HashTable(kk))
+        got = ops.conv_k3_h2(ops.split_h2(f[:n].to(DEV)), nb, pw, b.to(DEV), relu=True)[0]
+        assert _rel_err(got, torch.relu(S.conv_k3(f[:n], cc, 1, w, b))) < H2_TOL
+
+
+@pytest.mark.parametrize("cout", [1, 4, 8, 16, 32])
+def test_conv_k3_octet_h2_vs_oracle(cout):
+    """full-octet h2 kernels (halo of h2 rows in shared memory, parent's map) == oracle on the 8-child expansion."""
+    cin = 16
+    par = _surface()[:6007]
+    par[:, 1:] *= 2
+    pkeys, _ = ops.argsort_u64(_keys(par, 2))
+    pnbr = ops.kernel_map_k3(pkeys, ops.HashTable(pkeys))
+    c = ops.unpack_keys(ops.upsample_keys(pkeys), 1).cpu().numpy()
+    g = torch.Generator().manual_seed(cin * 11 + cout)
+    f = torch.randn(len(c), cin, generator=g) * 3.0
+    w = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    b = torch.randn(1, cout, generator=g)
+    ref = S.conv_k3(f, c, 1, w, b)
+    assert ops.octet_h2_supported(cin, cout)
+    pw = ops.PackedK3H2(w.to(DEV))
+    xh = ops.split_h2(f.to(DEV))
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    got, got_h = ops.conv_k3_octet_h2(xh, pnbr, pw, b.to(DEV), want_h2=cout % 4 == 0, overflow=flag)
+    assert _rel_err(got, ref) < H2_TOL
+    if cout % 4 == 0:
+        assert _rel_err(ops.join_h2(got_h), ref) < H2_TOL
+        res = torch.randn(len(c), cout, generator=g)
+        wide = torch.full((len(c), cout + 8), -7.0, device=DEV)
+        wide_h = torch.full((len(c), cout + 8), 5, dtype=torch.int32, device=DEV)
+        ops.conv_k3_octet_h2(xh, pnbr, pw, b.to(DEV), residual=res.to(DEV), relu=True, out=wide[:, 4:4 + cout], out_h2=wide_h[:, 4:4 + cout])
+        want = torch.relu(ref + res)
+        assert _rel_err(wide[:, 4:4 + cout], want) < H2_TOL and _rel_err(ops.join_h2(wide_h[:, 4:4 + cout]), want) < H2_TOL
+        assert (wide[:, :4] == -7).all() and (wide[:, 4 + cout:] == -7).all()
+        assert (wide_h[:, :4] == 5).all() and (wide_h[:, 4 + cout:] == 5).all()
+        wide_in = torch.zeros((len(c), cin + 4), dtype=torch.int32, device=DEV)
+        wide_in[:, 4:] = xh
+        assert _rel_err(ops.conv_k3_octet_h2(wide_in[:, 4:], pnbr, pw, b.to(DEV))[0], ref) < H2_TOL
+    assert int(flag.item()) == 0
+    for n_par in (1, 3, 31, 33, 257):                             # tile tails, fewer tiles than SMs
+        pk = pkeys[:n_par].contiguous()
+        nb = ops.kernel_map_k3(pk, ops.HashTable(pk))
+        cc = ops.unpack_keys(ops.upsample_keys(pk), 1).cpu().numpy()
+        got = ops.conv_k3_octet_h2(ops.split_h2(f[:8 * n_par].to(DEV)), nb, pw, b.to(DEV), relu=True)[0]
+        assert _rel_err(got, torch.relu(S.conv_k3(f[:8 * n_par], cc, 1, w, b))) < H2_TOL
+
+
+def test_conv_k3_h2_overflow_flag_and_small_weights():
+    """tiny weights keep their precision through the power-of-two scale; an output beyond the f16 range raises the flag."""
+    c = _surface()[:4001]
+    keys = _keys(c)
+    nbr = ops.kernel_map_k3(keys, ops.HashTable(keys))
+    g = torch.Generator().manual_seed(5)
+    f = torch.randn(len(c), 16, generator=g)
+    w = torch.randn(27, 16, 16, generator=g) * 1e-4
+    ref = S.conv_k3(f, c, 1, w, None)
+    got = ops.conv_k3_h2(ops.split_h2(f.to(DEV)), nbr, ops.PackedK3H2(w.to(DEV)))[0]
+    assert _rel_err(got, ref) < H2_TOL
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    big = ops.PackedK3H2((w * 1e8).to(DEV))
+    ops.conv_k3_h2(ops.split_h2(f.to(DEV)), nbr, big, want_h2=True, overflow=flag)
+    assert int(flag.item()) == 1
+
+
 def test_conv_k3_surface_and_ragged_sizes():
     c = _surface()
     keys = _keys(c)

@@ -1,0 +1,146 @@
+// Micro-benchmark + correctness check of conv_k3_h2_kernel variants (pre-split f16 features, HMMA.16816) against
+// conv_k3_mma_kernel (3xTF32) on a kernel map dumped by tools/profile_conv.py --dump (real vox10 decoder level).
+// Build here: tools/build_h2.sh "RUNH(16,16,false,4,2,8,2) ..."; run on the GPU box: tools/run_h2.sh
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <string>
+#include <algorithm>
+#include "../pcgcv2_b200/csrc/conv_mma.cuh"
+#include "../pcgcv2_b200/csrc/conv_h2.cuh"
+
+namespace pcgc { void set_error(const char *, ...) {} std::atomic<uint64_t> g_launches{0}; }
+using namespace pcgc;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+static float *g_flush;
+static int64_t g_n, g_pairs;
+static float *g_in, *g_out, *g_ref, *g_w, *g_packed, *g_bias, *g_res, *g_join;
+static uint32_t *g_in_h2, *g_out_h2;
+static int *g_over;
+static const int32_t *g_nbr;
+static int g_ref_cin = -1, g_ref_cout = -1;
+static std::vector<float> h_ref, h_out;
+
+template <typename K, typename... Args>
+static float time_kernel(K kern, int grid, int threads, size_t smem, Args... args) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e9;
+    for (int it = 0; it < 4; ++it) {
+        CK(cudaMemsetAsync(g_flush, it, 256u << 20));
+        cudaEventRecord(a);
+        kern<<<grid, threads, smem>>>(args...);
+        cudaEventRecord(b);
+        CK(cudaEventSynchronize(b));
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        if (it > 0) best = std::min(best, ms);
+    }
+    CK(cudaGetLastError());
+    return best;
+}
+
+template <int CIN, int COUT>
+static void reference() {
+    if (g_ref_cin == CIN && g_ref_cout == COUT) return;
+    using C = MmaCfg<CIN, COUT>;
+    auto kern = conv_k3_mma_kernel<CIN, COUT>;
+    size_t smem = C::smem_bytes();
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, smem));
+    pack_weights_mma_kernel<<<64, 256>>>(g_w, 27, CIN, COUT, g_packed);
+    int64_t tiles = (g_n + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
+    int grid = (int)std::min<int64_t>(tiles, (int64_t)148 * nb);
+    float ms = time_kernel(kern, grid, 256, smem, (const float *)g_in, CIN, g_nbr, g_n, (const float *)g_packed, (const float *)g_bias,
+                           (const float *)g_res, COUT, g_ref, COUT, 1);
+    h_ref.resize((size_t)g_n * COUT);
+    CK(cudaMemcpy(h_ref.data(), g_ref, h_ref.size() * 4, cudaMemcpyDeviceToHost));
+    g_ref_cin = CIN; g_ref_cout = COUT;
+    split_h2_kernel<<<148 * 8, 256>>>(g_in, CIN, g_n, CIN, g_in_h2, CIN, g_over, 1);
+    CK(cudaDeviceSynchronize());
+    printf("%-34s                               %.4f ms   (3xTF32 mma.sync kernel)\n",
+           (std::to_string(CIN) + "x" + std::to_string(COUT) + " mma ref").c_str(), ms);
+}
+
+static double compare(const std::vector<float> &a, const std::vector<float> &b) {
+    double maxd = 0, maxr = 0;
+    for (size_t i = 0; i < a.size(); ++i) {
+        double d = fabs((double)a[i] - (double)b[i]);
+        if (!(d <= maxd)) maxd = d;
+        maxr = std::max(maxr, fabs((double)b[i]));
+    }
+    return maxd / maxr;
+}
+
+template <int CIN, int COUT, bool NT, int RG, int D, int WARPS, int MINB>
+static void run(const char *name) {
+    reference<CIN, COUT>();
+    using C = H2Cfg<CIN, COUT, NT, RG, D, WARPS>;
+    auto kern = conv_k3_h2_kernel<CIN, COUT, NT, RG, D, WARPS, MINB>;
+    size_t smem = C::smem_bytes();
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, smem));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+    const float scale = 16384.f / 0.05f > 0 ? 131072.f : 1.f;      // weights are in +-0.05: 0.05 * 2^17 = 6554
+    pack_weights_h2_kernel<<<64, 256>>>(g_w, 27, CIN, COUT, NT ? 1 : 0, scale, (uint32_t *)g_packed);
+    CK(cudaMemset(g_out, 0xff, (size_t)g_n * COUT * 4));
+    CK(cudaMemset(g_out_h2, 0xff, (size_t)g_n * 64 * 4));
+    CK(cudaMemset(g_over, 0, 4));
+    int64_t tiles = (g_n + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
+    int grid = (int)std::min<int64_t>(tiles, (int64_t)148 * nb);
+    const bool h2out = COUT % 4 == 0;
+    float ms = time_kernel(kern, grid, C::THREADS, smem, (const uint32_t *)g_in_h2, CIN, g_nbr, g_n, (const uint32_t *)g_packed, 1.f / scale,
+                           (const float *)g_bias, (const float *)g_res, COUT, g_out, COUT, h2out ? g_out_h2 : nullptr, COUT, 1, g_over);
+    float ms_noh2 = time_kernel(kern, grid, C::THREADS, smem, (const uint32_t *)g_in_h2, CIN, g_nbr, g_n, (const uint32_t *)g_packed, 1.f / scale,
+                                (const float *)g_bias, (const float *)g_res, COUT, g_out, COUT, (uint32_t *)nullptr, COUT, 1, g_over);
+    h_out.resize((size_t)g_n * COUT);
+    CK(cudaMemcpy(h_out.data(), g_out, h_out.size() * 4, cudaMemcpyDeviceToHost));
+    const double rel = compare(h_out, h_ref);
+    double rel2 = 0;
+    if (h2out) {
+        join_h2_kernel<<<148 * 8, 256>>>(g_out_h2, COUT, g_n, COUT, g_join, COUT);
+        CK(cudaMemcpy(h_out.data(), g_join, h_out.size() * 4, cudaMemcpyDeviceToHost));
+        rel2 = compare(h_out, h_ref);
+    }
+    int over = 0; CK(cudaMemcpy(&over, g_over, 4, cudaMemcpyDeviceToHost));
+    const double alg = 4.0 * g_n * (CIN + COUT) + 8.0 * g_pairs + 4.0 * 27 * CIN * COUT, flops = 2.0 * g_pairs * CIN * COUT;
+    printf("%-38s regs %3d ctas/SM %d smem %6zu  %.4f ms (fp32 only %.4f)  %5.0f GB/s alg  %5.1f TFLOP/s  err %.2e h2 %.2e over %d %s\n", name,
+           fa.numRegs, nb, smem, ms, ms_noh2, alg / ms_noh2 / 1e6, flops / ms_noh2 / 1e9, rel, rel2, over, (rel < 3e-6 && rel2 < 3e-6) ? "ok" : "MISMATCH");
+}
+
+int main(int argc, char **argv) {
+    FILE *f = fopen(argc > 1 ? argv[1] : "/tmp/nbr.bin", "rb");
+    if (!f) { printf("no map dump\n"); return 1; }
+    int64_t n, pairs;
+    if (fread(&n, 8, 1, f) != 1 || fread(&pairs, 8, 1, f) != 1) return 1;
+    std::vector<int32_t> h(27 * n);
+    if (fread(h.data(), 4, 27 * n, f) != (size_t)(27 * n)) return 1;
+    fclose(f);
+    printf("rows %lld pairs %lld\n", (long long)n, (long long)pairs);
+    g_n = n; g_pairs = pairs;
+    int32_t *nbr; CK(cudaMalloc(&nbr, 27 * n * 4)); CK(cudaMemcpy(nbr, h.data(), 27 * n * 4, cudaMemcpyHostToDevice));
+    g_nbr = nbr;
+    CK(cudaMalloc(&g_flush, 256u << 20));
+    constexpr int MAXC = 64;
+    CK(cudaMalloc(&g_in, n * MAXC * 4)); CK(cudaMalloc(&g_out, n * MAXC * 4)); CK(cudaMalloc(&g_ref, n * MAXC * 4));
+    CK(cudaMalloc(&g_res, n * MAXC * 4)); CK(cudaMalloc(&g_join, n * MAXC * 4));
+    CK(cudaMalloc(&g_in_h2, n * MAXC * 4)); CK(cudaMalloc(&g_out_h2, n * MAXC * 4)); CK(cudaMalloc(&g_over, 4));
+    CK(cudaMalloc(&g_w, 27 * MAXC * MAXC * 4)); CK(cudaMalloc(&g_packed, 27 * MAXC * MAXC * 8 + 1024)); CK(cudaMalloc(&g_bias, MAXC * 4));
+    std::vector<float> hin(n * MAXC);
+    for (auto &v : hin) v = ((float)rand() / RAND_MAX - 0.3f) * 8.f;
+    CK(cudaMemcpy(g_in, hin.data(), n * MAXC * 4, cudaMemcpyHostToDevice));
+    for (auto &v : hin) v = (float)rand() / RAND_MAX - 0.5f;
+    CK(cudaMemcpy(g_res, hin.data(), n * MAXC * 4, cudaMemcpyHostToDevice));
+    std::vector<float> hw(27 * MAXC * MAXC);
+    for (auto &v : hw) v = ((float)rand() / RAND_MAX - 0.5f) * 0.1f;
+    CK(cudaMemcpy(g_w, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<float> hb(MAXC);
+    for (auto &v : hb) v = (float)rand() / RAND_MAX - 0.5f;
+    CK(cudaMemcpy(g_bias, hb.data(), MAXC * 4, cudaMemcpyHostToDevice));
+#define RUNH(CIN, COUT, NT, RG, D, WARPS, MINB) run<CIN, COUT, NT, RG, D, WARPS, MINB>(#CIN "x" #COUT " " #NT " RG" #RG " D" #D " warps" #WARPS " minb" #MINB);
+#include "/tmp/variants_h2.h"
+    return 0;
+}

@@ -29,7 +29,7 @@ tm = T()
 for _ in range(reps):
     tm.mark("_")
     coords = torch.cat([torch.zeros((len(dev_coords), 1), dtype=torch.int32, device="cuda"), dev_coords], 1)
-    level0 = codec._sorted_input(coords); tm.mark("enc: pack+sort input")
+    level0, _ = codec._sorted_input(coords, False); tm.mark("enc: pack+sort input")
     y, level3, num_points = codec.analysis(level0); tm.mark("enc: analysis network (incl. maps)")
     c3 = ops.unpack_keys(level3.keys, 1)[:, 1:]; order = codec._canonical_order(c3); y = y[order].contiguous(); c3 = c3[order]
     sym, lo, hi = ops.eb_quantize(y); _, table = ops.eb_cdf_table(codec.eb_params, lo, hi)
