@@ -203,6 +203,21 @@ int pcgc_conv_k2s2_fwd(const float *in, int32_t in_ld, const uint64_t *in_keys, 
  * out[8*i + k] = in[i] @ W[k] + bias. */
 int pcgc_convT_k2s2_fwd(const float *in, int32_t in_ld, int64_t n_in, const float *weight, const float *bias,
                         int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, void *stream);
+/* a5/a6/a7 writing, next to the fp32 output, its pre-split half-precision copy (h2 format, see pcgc_split_h2) for a
+ * following h2 k=3 layer, fused into the epilogue.  Returns PCGC_ERR_INVALID for shapes whose kernel cannot pair
+ * output channels per lane (use pcgc_split_h2 on the fp32 output then). */
+int pcgc_conv_h2out_supported(int32_t kind /* 1: k=1, 2: k=2 s=2, 3: transposed k=2 s=2 */, int32_t cin, int32_t cout);
+int pcgc_conv_k1_fwd_h2out(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias,
+                           int32_t cin, int32_t cout, const float *residual, int32_t res_ld, float *out,
+                           int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t flags, int32_t *overflow,
+                           void *stream);
+int pcgc_conv_k2s2_fwd_h2out(const float *in, int32_t in_ld, const uint64_t *in_keys, const int32_t *child_rows,
+                             const int32_t *child_off, int64_t n_parents, const float *weight, const float *bias,
+                             int32_t cin, int32_t cout, float *out, int32_t out_ld, uint32_t *out_h2,
+                             int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream);
+int pcgc_convT_k2s2_fwd_h2out(const float *in, int32_t in_ld, int64_t n_in, const float *weight, const float *bias,
+                              int32_t cin, int32_t cout, float *out, int32_t out_ld, uint32_t *out_h2,
+                              int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream);
 
 /* ---- backward passes (row a16; MinkowskiEngine Convolution*Backward driven by trainer.py:136) -----
  * Input gradients of the k=3 and k=1 convolutions are forward convolutions of grad_out with the

@@ -69,6 +69,11 @@ SIGNATURES = {
     "pcgc_conv_k1_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),
     "pcgc_conv_k2s2_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_i32, c_p]),
     "pcgc_convT_k2s2_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_i32, c_p]),
+    "pcgc_conv_h2out_supported": (ctypes.c_int, [c_i32, c_i32, c_i32]),
+    "pcgc_conv_k1_fwd_h2out": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_p]),
+    "pcgc_conv_k2s2_fwd_h2out": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32,
+                                                 c_p, c_p]),
+    "pcgc_convT_k2s2_fwd_h2out": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_p]),
     "pcgc_conv_bwd_weight": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_i32, c_p, c_p]),
     "pcgc_conv_k2s2_bwd": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_i64, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_p]),
     "pcgc_convT_k2s2_bwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_p]),

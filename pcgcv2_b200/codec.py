@@ -76,6 +76,13 @@ class _F:
         self.f, self.h = f, h
 
 
+class _FullOctets:
+    full_octets = True
+
+
+_FULL = _FullOctets()            # "a full-octet level" for kernel-routing questions asked before the level exists
+
+
 class Codec:
     def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True, use_h2=True):
         self.device = torch.device(device)
@@ -194,8 +201,14 @@ class Codec:
             self._rec(name, y, level)
         return y
 
-    def _k1(self, name, x, relu=False, residual=None, out=None):
-        return ops.conv_k1(x, self.w[name + ".kernel"], self.w[name + ".bias"], residual=residual, relu=relu, out=out)
+    def _k1(self, name, x, relu=False, residual=None, out=None, out_h=None):
+        """k=1 layer on fp32 rows; ``out_h`` (a slice, or True): also write the h2 copy in the epilogue when the kernel can
+        (-> fp32 out, h2 out or None when the caller has to split)."""
+        w = self.w[name + ".kernel"]
+        if out_h is not None and self._h2_on and ops.h2out_supported("k1", w.shape[0], w.shape[1]):
+            return ops.conv_k1(x, w, self.w[name + ".bias"], residual=residual, relu=relu, out=out, out_h2=out_h,
+                               overflow=self._overflow)
+        return ops.conv_k1(x, w, self.w[name + ".bias"], residual=residual, relu=relu, out=out), None
 
     def _uses_h2(self, name, level):
         """the layer will run on an h2 kernel (gather or full-octet variant)."""
@@ -219,11 +232,23 @@ class Codec:
         if a_h2:                                                     # this producer writes its half of the h2 copy too
             out.h = torch.empty((x.f.shape[0], c), dtype=torch.int32, device=self.device)
         self._k3(prefix + ".conv0_1", a, level, residual=x.f[:, :h], out=out.f[:, :h], out_h=None if out.h is None else out.h[:, :h])
-        b = _F(self._k1(prefix + ".conv1_0", x.f, relu=True))
+        b = _F(*self._k1(prefix + ".conv1_0", x.f, relu=True, out_h=True if self._uses_h2(prefix + ".conv1_1", level) else None))
         cc = self._k3(prefix + ".conv1_1", b, level, relu=True)
-        self._k1(prefix + ".conv1_2", cc.f, residual=x.f[:, h:], out=out.f[:, h:])
+        if out.h is None and self._h2_on:                            # the block output always feeds an h2 layer
+            out.h = torch.empty((x.f.shape[0], c), dtype=torch.int32, device=self.device)
+            first_half_done = False
+        else:
+            first_half_done = out.h is not None
+        _, hh = self._k1(prefix + ".conv1_2", cc.f, residual=x.f[:, h:], out=out.f[:, h:],
+                         out_h=None if out.h is None else out.h[:, h:])
         if out.h is not None:
-            ops.split_h2(out.f[:, h:], out=out.h[:, h:], overflow=self._overflow)
+            if hh is None and not first_half_done:
+                ops.split_h2(out.f, out=out.h, overflow=self._overflow)
+            else:
+                if hh is None:
+                    ops.split_h2(out.f[:, h:], out=out.h[:, h:], overflow=self._overflow)
+                if not first_half_done:
+                    ops.split_h2(out.f[:, :h], out=out.h[:, :h], overflow=self._overflow)
         self._rec(prefix, out, level)
         return out
 
@@ -256,8 +281,12 @@ class Codec:
         level, sizes = level0, [len(level0)]
         for i in range(3):
             rows, off = down[i]
-            x = _F(ops.conv_k2s2(x.f, level.keys, rows, off, self.w[f"encoder.down{i}.kernel"],
-                                 self.w[f"encoder.down{i}.bias"], relu=True))
+            wd = self.w[f"encoder.down{i}.kernel"]
+            if self._h2_on and ops.h2out_supported("down", wd.shape[1], wd.shape[2]):    # the IRN's h2 layers read this
+                x = _F(*ops.conv_k2s2(x.f, level.keys, rows, off, wd, self.w[f"encoder.down{i}.bias"], relu=True, out_h2=True,
+                                      overflow=self._overflow))
+            else:
+                x = _F(ops.conv_k2s2(x.f, level.keys, rows, off, wd, self.w[f"encoder.down{i}.bias"], relu=True))
             level = levels[i + 1]
             self._rec(f"encoder.down{i}", x, level)
             for j in range(3):
@@ -270,7 +299,11 @@ class Codec:
         """autoencoder.py:251-273 with training=False -> (final level, classifier logits per scale)."""
         x, cls_list = y, []
         for i in range(3):
-            x = _F(ops.convT_k2s2(x, self.w[f"decoder.up{i}.kernel"], self.w[f"decoder.up{i}.bias"], relu=True))
+            wu = self.w[f"decoder.up{i}.kernel"]
+            if self._h2_on and self._uses_h2(f"decoder.conv{i}", _FULL) and ops.h2out_supported("up", wu.shape[1], wu.shape[2]):
+                x = _F(*ops.convT_k2s2(x, wu, self.w[f"decoder.up{i}.bias"], relu=True, out_h2=True, overflow=self._overflow))
+            else:
+                x = _F(ops.convT_k2s2(x, wu, self.w[f"decoder.up{i}.bias"], relu=True))
             level = _Level(ops.upsample_keys(level.keys), level.stride // 2, parent=level)    # full octets
             self._rec(f"decoder.up{i}", x, level)
             x = self._k3(f"decoder.conv{i}", x, level, relu=True, want_h=True)

@@ -191,52 +191,126 @@ int pcgc_conv_k3_fwd_tcgen05(const float *in, int32_t in_ld, const int32_t *nbr,
     return PCGC_ERR_INVALID;
 }
 
-int pcgc_conv_k1_fwd(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias, int32_t cin,
-                     int32_t cout, const float *residual, int32_t res_ld, float *out, int32_t out_ld, int32_t flags,
-                     void *stream) {
-    int rc = check_conv_args("pcgc_conv_k1_fwd", in, weight, out, n, cin, cout, in_ld, out_ld);
+static int conv_k1_impl(const char *who, const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias,
+                        int32_t cin, int32_t cout, const float *residual, int32_t res_ld, float *out, int32_t out_ld,
+                        int32_t flags, uint32_t *out_h2, int32_t out_h2_ld, int32_t *overflow, void *stream) {
+    int rc = check_conv_args(who, in, weight, out, n, cin, cout, in_ld, out_ld);
     if (rc || n == 0) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     rc = kNotHandled;
-#define CASE(CI) if (cin == CI) rc = k1_ci##CI(in, in_ld, n, weight, bias, cout, residual, res_ld, out, out_ld, flags, s);
+#define CASE(CI) if (cin == CI) rc = k1_ci##CI(in, in_ld, n, weight, bias, cout, residual, res_ld, out, out_ld, flags, s, out_h2, out_h2_ld, overflow);
     PCGC_FOR_CI(CASE)
 #undef CASE
     if (rc != kNotHandled) return rc;
+    PCGC_REQUIRE(!out_h2, "%s: no h2 output for shape %dx%d", who, cin, cout);
     conv_generic_kernel<<<grid_for(n * cout, 256, 8), 256, 0, s>>>(in, in_ld, nullptr, n, 1, weight, bias, cin, cout,
                                                                    residual, res_ld, out, out_ld, flags);
     return check_launch("conv_generic");
 }
 
-int pcgc_conv_k2s2_fwd(const float *in, int32_t in_ld, const uint64_t *in_keys, const int32_t *child_rows,
-                       const int32_t *child_off, int64_t n_parents, const float *weight, const float *bias,
-                       int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, void *stream) {
-    int rc = check_conv_args("pcgc_conv_k2s2_fwd", in, weight, out, n_parents, cin, cout, in_ld, out_ld);
+static int conv_k2s2_impl(const char *who, const float *in, int32_t in_ld, const uint64_t *in_keys, const int32_t *child_rows,
+                          const int32_t *child_off, int64_t n_parents, const float *weight, const float *bias, int32_t cin,
+                          int32_t cout, float *out, int32_t out_ld, int32_t flags, uint32_t *out_h2, int32_t out_h2_ld,
+                          int32_t *overflow, void *stream) {
+    int rc = check_conv_args(who, in, weight, out, n_parents, cin, cout, in_ld, out_ld);
     if (rc || n_parents == 0) return rc;
-    PCGC_REQUIRE(in_keys && child_rows && child_off, "pcgc_conv_k2s2_fwd: null map");
+    PCGC_REQUIRE(in_keys && child_rows && child_off, "%s: null map", who);
     cudaStream_t s = (cudaStream_t)stream;
     rc = kNotHandled;
-#define CASE(CI) if (cin == CI) rc = down_ci##CI(in, in_ld, in_keys, child_rows, child_off, n_parents, weight, bias, cout, out, out_ld, flags, s);
+#define CASE(CI) if (cin == CI) rc = down_ci##CI(in, in_ld, in_keys, child_rows, child_off, n_parents, weight, bias, cout, out, out_ld, flags, s, out_h2, out_h2_ld, overflow);
     PCGC_FOR_CI(CASE)
 #undef CASE
     if (rc != kNotHandled) return rc;
+    PCGC_REQUIRE(!out_h2, "%s: no h2 output for shape %dx%d", who, cin, cout);
     conv_down_generic_kernel<<<grid_for(n_parents * cout, 256, 8), 256, 0, s>>>(
         in, in_ld, in_keys, child_rows, child_off, n_parents, weight, bias, cin, cout, out, out_ld, flags);
     return check_launch("conv_down_generic");
 }
 
-int pcgc_convT_k2s2_fwd(const float *in, int32_t in_ld, int64_t n_in, const float *weight, const float *bias,
-                        int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, void *stream) {
-    int rc = check_conv_args("pcgc_convT_k2s2_fwd", in, weight, out, n_in, cin, cout, in_ld, out_ld);
+static int convT_k2s2_impl(const char *who, const float *in, int32_t in_ld, int64_t n_in, const float *weight, const float *bias,
+                           int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, uint32_t *out_h2,
+                           int32_t out_h2_ld, int32_t *overflow, void *stream) {
+    int rc = check_conv_args(who, in, weight, out, n_in, cin, cout, in_ld, out_ld);
     if (rc || n_in == 0) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     rc = kNotHandled;
-#define CASE(CI) if (cin == CI) rc = up_ci##CI(in, in_ld, n_in, weight, bias, cout, out, out_ld, flags, s);
+#define CASE(CI) if (cin == CI) rc = up_ci##CI(in, in_ld, n_in, weight, bias, cout, out, out_ld, flags, s, out_h2, out_h2_ld, overflow);
     PCGC_FOR_CI(CASE)
 #undef CASE
     if (rc != kNotHandled) return rc;
+    PCGC_REQUIRE(!out_h2, "%s: no h2 output for shape %dx%d", who, cin, cout);
     conv_up_generic_kernel<<<grid_for(n_in * 8 * cout, 256, 8), 256, 0, s>>>(in, in_ld, n_in, weight, bias, cin, cout,
                                                                             out, out_ld, flags);
     return check_launch("conv_up_generic");
+}
+
+// shapes whose row-lane kernel leaves every storing lane with an even number of finished channels (conv_rowlane.cuh)
+static bool rowlane_h2out_shape(int kind, int cin, int cout) {
+    auto listed = [](int c) { return c == 4 || c == 8 || c == 16 || c == 32 || c == 64 || c == 128; };
+    if (!listed(cin) || !listed(cout)) return false;
+    if (kind != 1 && (cin < 8 || cout < 8 || (size_t)8 * cin * cout * sizeof(float) > 160 * 1024)) return false;
+    int lpr = cin / 4, log_lpr = 0, tz = 0;
+    while ((1 << (log_lpr + 1)) <= lpr) ++log_lpr;
+    while (((cout >> tz) & 1) == 0) ++tz;
+    const int hs = log_lpr < tz ? log_lpr : tz;
+    return ((cout >> hs) % 2) == 0;
+}
+
+static int check_h2_out(const char *who, const uint32_t *out_h2, int32_t out_h2_ld, int32_t cout) {
+    PCGC_REQUIRE(out_h2 && cout % 4 == 0 && out_h2_ld >= cout && out_h2_ld % 4 == 0 && ((uintptr_t)out_h2 & 15) == 0,
+                 "%s: the h2 output needs cout %% 4 == 0 and 16-byte aligned rows", who);
+    return PCGC_OK;
+}
+
+int pcgc_conv_k1_fwd(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias, int32_t cin,
+                     int32_t cout, const float *residual, int32_t res_ld, float *out, int32_t out_ld, int32_t flags,
+                     void *stream) {
+    return conv_k1_impl("pcgc_conv_k1_fwd", in, in_ld, n, weight, bias, cin, cout, residual, res_ld, out, out_ld, flags, nullptr, 0,
+                        nullptr, stream);
+}
+
+int pcgc_conv_k2s2_fwd(const float *in, int32_t in_ld, const uint64_t *in_keys, const int32_t *child_rows,
+                       const int32_t *child_off, int64_t n_parents, const float *weight, const float *bias,
+                       int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, void *stream) {
+    return conv_k2s2_impl("pcgc_conv_k2s2_fwd", in, in_ld, in_keys, child_rows, child_off, n_parents, weight, bias, cin, cout, out,
+                          out_ld, flags, nullptr, 0, nullptr, stream);
+}
+
+int pcgc_convT_k2s2_fwd(const float *in, int32_t in_ld, int64_t n_in, const float *weight, const float *bias,
+                        int32_t cin, int32_t cout, float *out, int32_t out_ld, int32_t flags, void *stream) {
+    return convT_k2s2_impl("pcgc_convT_k2s2_fwd", in, in_ld, n_in, weight, bias, cin, cout, out, out_ld, flags, nullptr, 0, nullptr,
+                           stream);
+}
+
+int pcgc_conv_h2out_supported(int32_t kind, int32_t cin, int32_t cout) { return rowlane_h2out_shape(kind, cin, cout) ? 1 : 0; }
+
+// the same three layers writing, next to the fp32 output, its pre-split half-precision copy for a following h2 k=3 layer
+int pcgc_conv_k1_fwd_h2out(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias, int32_t cin,
+                           int32_t cout, const float *residual, int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2,
+                           int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream) {
+    int rc = check_h2_out("pcgc_conv_k1_fwd_h2out", out_h2, out_h2_ld, cout);
+    if (rc) return rc;
+    return conv_k1_impl("pcgc_conv_k1_fwd_h2out", in, in_ld, n, weight, bias, cin, cout, residual, res_ld, out, out_ld, flags, out_h2,
+                        out_h2_ld, overflow, stream);
+}
+
+int pcgc_conv_k2s2_fwd_h2out(const float *in, int32_t in_ld, const uint64_t *in_keys, const int32_t *child_rows,
+                             const int32_t *child_off, int64_t n_parents, const float *weight, const float *bias, int32_t cin,
+                             int32_t cout, float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t flags,
+                             int32_t *overflow, void *stream) {
+    int rc = check_h2_out("pcgc_conv_k2s2_fwd_h2out", out_h2, out_h2_ld, cout);
+    if (rc) return rc;
+    return conv_k2s2_impl("pcgc_conv_k2s2_fwd_h2out", in, in_ld, in_keys, child_rows, child_off, n_parents, weight, bias, cin, cout,
+                          out, out_ld, flags, out_h2, out_h2_ld, overflow, stream);
+}
+
+int pcgc_convT_k2s2_fwd_h2out(const float *in, int32_t in_ld, int64_t n_in, const float *weight, const float *bias, int32_t cin,
+                              int32_t cout, float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t flags,
+                              int32_t *overflow, void *stream) {
+    int rc = check_h2_out("pcgc_convT_k2s2_fwd_h2out", out_h2, out_h2_ld, cout);
+    if (rc) return rc;
+    return convT_k2s2_impl("pcgc_convT_k2s2_fwd_h2out", in, in_ld, n_in, weight, bias, cin, cout, out, out_ld, flags, out_h2, out_h2_ld,
+                           overflow, stream);
 }
 
 }  // extern "C"

@@ -14,12 +14,13 @@ constexpr int kNotHandled = 1;
     int mma_ci##CI(const float *in, int in_ld, const int32_t *nbr, int64_t n, const float *packed, const float *b, \
                    int cout, const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s);    \
     int k1_ci##CI(const float *in, int in_ld, int64_t n, const float *w, const float *b, int cout,                \
-                  const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s);                \
+                  const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s,                 \
+                  uint32_t *out_h2, int out_h2_ld, int *overflow);                                                 \
     int down_ci##CI(const float *in, int in_ld, const uint64_t *keys, const int32_t *rows, const int32_t *off,    \
                     int64_t np, const float *w, const float *b, int cout, float *out, int out_ld, int flags,       \
-                    cudaStream_t s);                                                                               \
+                    cudaStream_t s, uint32_t *out_h2, int out_h2_ld, int *overflow);                               \
     int up_ci##CI(const float *in, int in_ld, int64_t n_in, const float *w, const float *b, int cout, float *out, \
-                  int out_ld, int flags, cudaStream_t s);
+                  int out_ld, int flags, cudaStream_t s, uint32_t *out_h2, int out_h2_ld, int *overflow);
 PCGC_FOR_CI(PCGC_DECL)
 #undef PCGC_DECL
 

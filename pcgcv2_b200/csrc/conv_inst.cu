@@ -41,15 +41,17 @@ static inline int ctas_per_sm_for(size_t smem) {
 
 template <int CIN, int COUT, int KVOL>
 static int launch_rowlane(const float *in, int in_ld, const int32_t *nbr, int64_t n, const float *w, const float *b,
-                          const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s) {
+                          const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s,
+                          uint32_t *oh = nullptr, int oh_ld = 0, int *ovf = nullptr) {
     using R = RowLane<CIN, COUT>;
+    if (oh && R::FC % 2 != 0) return kNotHandled;          // the h2 copy needs channel pairs per storing lane
     const size_t smem = R::weight_smem_bytes(KVOL);
     auto kern = conv_rowlane_kernel<CIN, COUT, KVOL>;
     int rc = prepare_smem(kern, smem);
     if (rc) return rc;
     const int rows_per_block = (kRowLaneThreads / 32) * R::RPW;
     kern<<<grid_for(n, rows_per_block, ctas_per_sm_for(smem)), kRowLaneThreads, smem, s>>>(
-        in, in_ld, nbr, n, w, b, res, res_ld, out, out_ld, flags, aligned_bits(in, in_ld, out, out_ld, res, res_ld));
+        in, in_ld, nbr, n, w, b, res, res_ld, out, out_ld, flags, aligned_bits(in, in_ld, out, out_ld, res, res_ld), oh, oh_ld, ovf);
     return check_launch("conv_rowlane");
 }
 
@@ -68,29 +70,32 @@ static int launch_tile(const float *in, int in_ld, const int32_t *nbr, int64_t n
 
 template <int CIN, int COUT>
 static int launch_down(const float *in, int in_ld, const uint64_t *keys, const int32_t *rows, const int32_t *off,
-                       int64_t np, const float *w, const float *b, float *out, int out_ld, int flags, cudaStream_t s) {
+                       int64_t np, const float *w, const float *b, float *out, int out_ld, int flags, cudaStream_t s,
+                       uint32_t *oh, int oh_ld, int *ovf) {
     using R = RowLane<CIN, COUT>;
+    if (oh && R::FC % 2 != 0) return kNotHandled;
     const size_t smem = R::weight_smem_bytes(8);
     auto kern = conv_down_rowlane_kernel<CIN, COUT>;
     int rc = prepare_smem(kern, smem);
     if (rc) return rc;
     const int rows_per_block = (kRowLaneThreads / 32) * R::RPW;
     kern<<<grid_for(np, rows_per_block, ctas_per_sm_for(smem)), kRowLaneThreads, smem, s>>>(
-        in, in_ld, keys, rows, off, np, w, b, out, out_ld, flags, aligned_bits(in, in_ld, out, out_ld, nullptr, 0));
+        in, in_ld, keys, rows, off, np, w, b, out, out_ld, flags, aligned_bits(in, in_ld, out, out_ld, nullptr, 0), oh, oh_ld, ovf);
     return check_launch("conv_down_rowlane");
 }
 
 template <int CIN, int COUT>
 static int launch_up(const float *in, int in_ld, int64_t n_in, const float *w, const float *b, float *out, int out_ld,
-                     int flags, cudaStream_t s) {
+                     int flags, cudaStream_t s, uint32_t *oh, int oh_ld, int *ovf) {
     using R = RowLane<CIN, COUT>;
+    if (oh && R::FC % 2 != 0) return kNotHandled;
     const size_t smem = R::weight_smem_bytes(8);
     auto kern = conv_up_rowlane_kernel<CIN, COUT>;
     int rc = prepare_smem(kern, smem);
     if (rc) return rc;
     const int rows_per_block = (kRowLaneThreads / 32) * R::RPW;
     kern<<<grid_for(n_in, rows_per_block, ctas_per_sm_for(smem)), kRowLaneThreads, smem, s>>>(
-        in, in_ld, n_in, w, b, out, out_ld, flags, aligned_bits(in, in_ld, out, out_ld, nullptr, 0));
+        in, in_ld, n_in, w, b, out, out_ld, flags, aligned_bits(in, in_ld, out, out_ld, nullptr, 0), oh, oh_ld, ovf);
     return check_launch("conv_up_rowlane");
 }
 
@@ -111,25 +116,26 @@ static int k3_case(const float *in, int in_ld, const int32_t *nbr, int64_t n, co
 
 template <int CO>
 static int k1_case(const float *in, int in_ld, int64_t n, const float *w, const float *b, const float *res, int res_ld,
-                   float *out, int out_ld, int flags, cudaStream_t s) {
+                   float *out, int out_ld, int flags, cudaStream_t s, uint32_t *oh, int oh_ld, int *ovf) {
     if constexpr (CI >= 4)
-        return launch_rowlane<CI, CO, 1>(in, in_ld, nullptr, n, w, b, res, res_ld, out, out_ld, flags, s);
+        return launch_rowlane<CI, CO, 1>(in, in_ld, nullptr, n, w, b, res, res_ld, out, out_ld, flags, s, oh, oh_ld, ovf);
     return kNotHandled;
 }
 
 template <int CO>
 static int down_case(const float *in, int in_ld, const uint64_t *keys, const int32_t *rows, const int32_t *off,
-                     int64_t np, const float *w, const float *b, float *out, int out_ld, int flags, cudaStream_t s) {
+                     int64_t np, const float *w, const float *b, float *out, int out_ld, int flags, cudaStream_t s,
+                     uint32_t *oh, int oh_ld, int *ovf) {
     if constexpr (CI >= 8 && CO >= 8 && RowLane<CI, CO>::weight_smem_bytes(8) <= kRowLaneSmemLimit)
-        return launch_down<CI, CO>(in, in_ld, keys, rows, off, np, w, b, out, out_ld, flags, s);
+        return launch_down<CI, CO>(in, in_ld, keys, rows, off, np, w, b, out, out_ld, flags, s, oh, oh_ld, ovf);
     return kNotHandled;
 }
 
 template <int CO>
 static int up_case(const float *in, int in_ld, int64_t n_in, const float *w, const float *b, float *out, int out_ld,
-                   int flags, cudaStream_t s) {
+                   int flags, cudaStream_t s, uint32_t *oh, int oh_ld, int *ovf) {
     if constexpr (CI >= 8 && CO >= 8 && RowLane<CI, CO>::weight_smem_bytes(8) <= kRowLaneSmemLimit)
-        return launch_up<CI, CO>(in, in_ld, n_in, w, b, out, out_ld, flags, s);
+        return launch_up<CI, CO>(in, in_ld, n_in, w, b, out, out_ld, flags, s, oh, oh_ld, ovf);
     return kNotHandled;
 }
 
@@ -193,8 +199,9 @@ int PCGC_CAT(mma_ci, PCGC_CI)(const float *in, int in_ld, const int32_t *nbr, in
 }
 
 int PCGC_CAT(k1_ci, PCGC_CI)(const float *in, int in_ld, int64_t n, const float *w, const float *b, int cout,
-                             const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s) {
-#define CASE(CO) if (cout == CO) return k1_case<CO>(in, in_ld, n, w, b, res, res_ld, out, out_ld, flags, s);
+                             const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s,
+                             uint32_t *oh, int oh_ld, int *ovf) {
+#define CASE(CO) if (cout == CO) return k1_case<CO>(in, in_ld, n, w, b, res, res_ld, out, out_ld, flags, s, oh, oh_ld, ovf);
     PCGC_FOR_CO(CASE)
 #undef CASE
     return kNotHandled;
@@ -202,16 +209,16 @@ int PCGC_CAT(k1_ci, PCGC_CI)(const float *in, int in_ld, int64_t n, const float 
 
 int PCGC_CAT(down_ci, PCGC_CI)(const float *in, int in_ld, const uint64_t *keys, const int32_t *rows,
                                const int32_t *off, int64_t np, const float *w, const float *b, int cout, float *out,
-                               int out_ld, int flags, cudaStream_t s) {
-#define CASE(CO) if (cout == CO) return down_case<CO>(in, in_ld, keys, rows, off, np, w, b, out, out_ld, flags, s);
+                               int out_ld, int flags, cudaStream_t s, uint32_t *oh, int oh_ld, int *ovf) {
+#define CASE(CO) if (cout == CO) return down_case<CO>(in, in_ld, keys, rows, off, np, w, b, out, out_ld, flags, s, oh, oh_ld, ovf);
     PCGC_FOR_CO(CASE)
 #undef CASE
     return kNotHandled;
 }
 
 int PCGC_CAT(up_ci, PCGC_CI)(const float *in, int in_ld, int64_t n_in, const float *w, const float *b, int cout,
-                             float *out, int out_ld, int flags, cudaStream_t s) {
-#define CASE(CO) if (cout == CO) return up_case<CO>(in, in_ld, n_in, w, b, out, out_ld, flags, s);
+                             float *out, int out_ld, int flags, cudaStream_t s, uint32_t *oh, int oh_ld, int *ovf) {
+#define CASE(CO) if (cout == CO) return up_case<CO>(in, in_ld, n_in, w, b, out, out_ld, flags, s, oh, oh_ld, ovf);
     PCGC_FOR_CO(CASE)
 #undef CASE
     return kNotHandled;

@@ -10,6 +10,7 @@
 // "read each map entry once, gather rows through L1/L2, write each output once".
 #pragma once
 #include "common.cuh"
+#include "conv_h2.cuh"   // split_pair_h2: optional pre-split half-precision copy of the output
 
 namespace pcgc {
 
@@ -123,13 +124,14 @@ template <int CIN, int COUT>
 __device__ __forceinline__ void finish_row(float (&acc)[COUT], int l, bool valid, int64_t row,
                                            const float *__restrict__ bias, const float *__restrict__ residual,
                                            int res_ld, float *__restrict__ out, int out_ld, int flags,
-                                           bool io_aligned) {
+                                           bool io_aligned, uint32_t *__restrict__ out_h2 = nullptr, int out_h2_ld = 0,
+                                           bool *over = nullptr) {
     using R = RowLane<CIN, COUT>;
     int base = 0;
     LaneReduce<R::LPR / 2, COUT>::run(acc, l, base);
-    if (!valid || (l & ((1 << R::AS) - 1)) != 0) return;
+    const bool store = valid && (l & ((1 << R::AS) - 1)) == 0;
     float *o = out + row * out_ld + base;
-    const float *r = residual ? residual + row * res_ld + base : nullptr;
+    const float *r = (residual && store) ? residual + row * res_ld + base : nullptr;
 #pragma unroll
     for (int i = 0; i < R::FC; ++i) {
         float v = acc[i];
@@ -138,6 +140,33 @@ __device__ __forceinline__ void finish_row(float (&acc)[COUT], int l, bool valid
         if (flags & PCGC_EPI_RELU) v = fmaxf(v, 0.f);
         acc[i] = v;
     }
+    if constexpr (R::FC % 2 == 0) {        // h2 copy for the next k=3 layer: 16-byte groups {hi01 hi23 lo01 lo23} (conv_h2.cuh)
+        if (out_h2) {                      // (uniform over the warp)
+            uint32_t *oh = out_h2 + row * out_h2_ld;
+            if constexpr (R::FC % 4 == 0) {
+                if (store) {
+#pragma unroll
+                    for (int i = 0; i < R::FC; i += 4) {
+                        uint4 q;
+                        split_pair_h2(acc[i], acc[i + 1], q.x, q.z);
+                        split_pair_h2(acc[i + 2], acc[i + 3], q.y, q.w);
+                        *over |= fabsf(acc[i]) > kH2Limit || fabsf(acc[i + 1]) > kH2Limit || fabsf(acc[i + 2]) > kH2Limit ||
+                                 fabsf(acc[i + 3]) > kH2Limit;
+                        *reinterpret_cast<uint4 *>(oh + base + i) = q;
+                    }
+                }
+            } else {                       // FC == 2: the lane one halving step away holds the other pair of the group
+                uint32_t hi, lo;
+                split_pair_h2(acc[0], acc[1], hi, lo);
+                const uint32_t phi = __shfl_xor_sync(0xffffffffu, hi, 1 << R::AS), plo = __shfl_xor_sync(0xffffffffu, lo, 1 << R::AS);
+                if (store) {
+                    *over |= fabsf(acc[0]) > kH2Limit || fabsf(acc[1]) > kH2Limit;
+                    if ((base & 2) == 0) *reinterpret_cast<uint4 *>(oh + base) = make_uint4(hi, phi, lo, plo);
+                }
+            }
+        }
+    }
+    if (!store) return;
     if constexpr (R::FC % 4 == 0) {
         if (io_aligned) {
 #pragma unroll
@@ -158,9 +187,10 @@ __global__ void __launch_bounds__(kRowLaneThreads)
 conv_rowlane_kernel(const float *__restrict__ in, int in_ld, const int32_t *__restrict__ nbr, int64_t n,
                     const float *__restrict__ weight, const float *__restrict__ bias,
                     const float *__restrict__ residual, int res_ld, float *__restrict__ out, int out_ld, int flags,
-                    int aligned_bits) {
+                    int aligned_bits, uint32_t *__restrict__ out_h2, int out_h2_ld, int *__restrict__ overflow) {
     using R = RowLane<CIN, COUT>;
     extern __shared__ __align__(16) float ws[];
+    bool over = false;
     load_weights_rowlane<CIN, COUT>(weight, KVOL, ws);
     __syncthreads();
     const bool in_aligned = aligned_bits & 1, io_aligned = aligned_bits & 2;
@@ -193,8 +223,9 @@ conv_rowlane_kernel(const float *__restrict__ in, int in_ld, const int32_t *__re
                     if (__any_sync(0xffffffffu, idx[j] >= 0)) accum_rowlane<CIN, COUT>(acc, v[j], ws, k0 + j, l);
             }
         }
-        finish_row<CIN, COUT>(acc, l, valid, row, bias, residual, res_ld, out, out_ld, flags, io_aligned);
+        finish_row<CIN, COUT>(acc, l, valid, row, bias, residual, res_ld, out, out_ld, flags, io_aligned, out_h2, out_h2_ld, &over);
     }
+    if (over && overflow) *overflow = 1;
 }
 
 // ---- k=2 stride-2 down: one output row per parent, <= 8 children from the CSR map ---------
@@ -203,9 +234,11 @@ __global__ void __launch_bounds__(kRowLaneThreads)
 conv_down_rowlane_kernel(const float *__restrict__ in, int in_ld, const uint64_t *__restrict__ in_keys,
                          const int32_t *__restrict__ child_rows, const int32_t *__restrict__ child_off,
                          int64_t n_parents, const float *__restrict__ weight, const float *__restrict__ bias,
-                         float *__restrict__ out, int out_ld, int flags, int aligned_bits) {
+                         float *__restrict__ out, int out_ld, int flags, int aligned_bits,
+                         uint32_t *__restrict__ out_h2, int out_h2_ld, int *__restrict__ overflow) {
     using R = RowLane<CIN, COUT>;
     extern __shared__ __align__(16) float ws[];
+    bool over = false;
     load_weights_rowlane<CIN, COUT>(weight, 8, ws);
     __syncthreads();
     const bool in_aligned = aligned_bits & 1, io_aligned = aligned_bits & 2;
@@ -235,8 +268,9 @@ conv_down_rowlane_kernel(const float *__restrict__ in, int in_ld, const uint64_t
                 accum_rowlane<CIN, COUT>(acc, v, ws, kk[j], l);
             }
         }
-        finish_row<CIN, COUT>(acc, l, valid, row, bias, nullptr, 0, out, out_ld, flags, io_aligned);
+        finish_row<CIN, COUT>(acc, l, valid, row, bias, nullptr, 0, out, out_ld, flags, io_aligned, out_h2, out_h2_ld, &over);
     }
+    if (over && overflow) *overflow = 1;
 }
 
 // ---- generative k=2 stride-2 up: input row i -> output rows 8i .. 8i+7 ----------------------
@@ -244,9 +278,10 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(kRowLaneThreads)
 conv_up_rowlane_kernel(const float *__restrict__ in, int in_ld, int64_t n_in, const float *__restrict__ weight,
                        const float *__restrict__ bias, float *__restrict__ out, int out_ld, int flags,
-                       int aligned_bits) {
+                       int aligned_bits, uint32_t *__restrict__ out_h2, int out_h2_ld, int *__restrict__ overflow) {
     using R = RowLane<CIN, COUT>;
     extern __shared__ __align__(16) float ws[];
+    bool over = false;
     load_weights_rowlane<CIN, COUT>(weight, 8, ws);
     __syncthreads();
     const bool in_aligned = aligned_bits & 1, io_aligned = aligned_bits & 2;
@@ -264,9 +299,10 @@ conv_up_rowlane_kernel(const float *__restrict__ in, int in_ld, int64_t n_in, co
 #pragma unroll
             for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
             accum_rowlane<CIN, COUT>(acc, v, ws, k, l);
-            finish_row<CIN, COUT>(acc, l, valid, row * 8 + k, bias, nullptr, 0, out, out_ld, flags, io_aligned);
+            finish_row<CIN, COUT>(acc, l, valid, row * 8 + k, bias, nullptr, 0, out, out_ld, flags, io_aligned, out_h2, out_h2_ld, &over);
         }
     }
+    if (over && overflow) *overflow = 1;
 }
 
 }  // namespace pcgc

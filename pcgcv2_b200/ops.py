@@ -362,38 +362,71 @@ def conv_k3_octet_h2(feats_h2, parent_nbr, pw: PackedK3H2, bias=None, residual=N
     return out, out_h2
 
 
-def conv_k1(feats, weight, bias=None, residual=None, relu=False, out=None):
+def h2out_supported(kind: str, cin, cout) -> bool:
+    """kind in {"k1", "down", "up"}: the layer's kernel can write the h2 copy of its output in its epilogue."""
+    return bool(_lib.lib().pcgc_conv_h2out_supported({"k1": 1, "down": 2, "up": 3}[kind], int(cin), int(cout)))
+
+
+def _h2_out(out_h2, n, cout, device):
+    if out_h2 is None:
+        out_h2 = torch.empty((n, cout), dtype=torch.int32, device=device)
+    assert out_h2.shape[0] == n and out_h2.shape[1] == cout and out_h2.dtype == torch.int32 and out_h2.stride(1) == 1
+    return out_h2
+
+
+def conv_k1(feats, weight, bias=None, residual=None, relu=False, out=None, out_h2=None, overflow=None):
+    """out_h2: int32 [n, cout] tensor (or True to allocate one) that receives the h2 copy of the output -> (out, out_h2)."""
     feats = _feat(feats)
     n, cin = feats.shape
     assert weight.dim() == 2 and weight.shape[0] == cin and weight.is_contiguous()
     cout = weight.shape[1]
     out = _out_slice(out, n, cout, feats.device)
     residual = None if residual is None else _feat(residual)
+    if out_h2 is not None:
+        out_h2 = _h2_out(None if out_h2 is True else out_h2, n, cout, feats.device)
+        check(_lib.lib().pcgc_conv_k1_fwd_h2out(_p(feats), feats.stride(0), n, _p(weight), _p(bias), cin, cout, _p(residual),
+                                                0 if residual is None else residual.stride(0), _p(out), out.stride(0),
+                                                _p(out_h2), out_h2.stride(0), EPI_RELU if relu else 0, _p(overflow), _stream()),
+              "pcgc_conv_k1_fwd_h2out")
+        return out, out_h2
     check(_lib.lib().pcgc_conv_k1_fwd(_p(feats), feats.stride(0), n, _p(weight), _p(bias), cin, cout, _p(residual),
                                       0 if residual is None else residual.stride(0), _p(out), out.stride(0),
                                       EPI_RELU if relu else 0, _stream()), "pcgc_conv_k1_fwd")
     return out
 
 
-def conv_k2s2(feats, in_keys, child_rows, child_off, weight, bias=None, relu=False, out=None):
+def conv_k2s2(feats, in_keys, child_rows, child_off, weight, bias=None, relu=False, out=None, out_h2=None, overflow=None):
     feats = _feat(feats)
     cin = feats.shape[1]
     n_par = child_off.shape[0] - 1
     cout = weight.shape[2]
     assert weight.shape[0] == 8 and weight.shape[1] == cin and weight.is_contiguous()
     out = _out_slice(out, n_par, cout, feats.device)
+    if out_h2 is not None:
+        out_h2 = _h2_out(None if out_h2 is True else out_h2, n_par, cout, feats.device)
+        check(_lib.lib().pcgc_conv_k2s2_fwd_h2out(_p(feats), feats.stride(0), _p(in_keys), _p(child_rows), _p(child_off), n_par,
+                                                  _p(weight), _p(bias), cin, cout, _p(out), out.stride(0), _p(out_h2),
+                                                  out_h2.stride(0), EPI_RELU if relu else 0, _p(overflow), _stream()),
+              "pcgc_conv_k2s2_fwd_h2out")
+        return out, out_h2
     check(_lib.lib().pcgc_conv_k2s2_fwd(_p(feats), feats.stride(0), _p(in_keys), _p(child_rows), _p(child_off), n_par,
                                         _p(weight), _p(bias), cin, cout, _p(out), out.stride(0),
                                         EPI_RELU if relu else 0, _stream()), "pcgc_conv_k2s2_fwd")
     return out
 
 
-def convT_k2s2(feats, weight, bias=None, relu=False, out=None):
+def convT_k2s2(feats, weight, bias=None, relu=False, out=None, out_h2=None, overflow=None):
     feats = _feat(feats)
     n, cin = feats.shape
     cout = weight.shape[2]
     assert weight.shape[0] == 8 and weight.shape[1] == cin and weight.is_contiguous()
     out = _out_slice(out, 8 * n, cout, feats.device)
+    if out_h2 is not None:
+        out_h2 = _h2_out(None if out_h2 is True else out_h2, 8 * n, cout, feats.device)
+        check(_lib.lib().pcgc_convT_k2s2_fwd_h2out(_p(feats), feats.stride(0), n, _p(weight), _p(bias), cin, cout, _p(out),
+                                                   out.stride(0), _p(out_h2), out_h2.stride(0), EPI_RELU if relu else 0,
+                                                   _p(overflow), _stream()), "pcgc_convT_k2s2_fwd_h2out")
+        return out, out_h2
     check(_lib.lib().pcgc_convT_k2s2_fwd(_p(feats), feats.stride(0), n, _p(weight), _p(bias), cin, cout, _p(out),
                                          out.stride(0), EPI_RELU if relu else 0, _stream()), "pcgc_convT_k2s2_fwd")
     return out

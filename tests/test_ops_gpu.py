@@ -418,6 +418,47 @@ def test_conv_k3_octet_h2_vs_oracle(cout):
         assert _rel_err(got, torch.relu(S.conv_k3(f[:8 * n_par], cc, 1, w, b))) < H2_TOL
 
 
+def test_rowlane_layers_write_h2_copy_in_epilogue():
+    """k=1 / k=2 s=2 / transposed k=2 s=2 with the fused h2 output: fp32 result unchanged, h2 copy == split of it."""
+    g = torch.Generator().manual_seed(9)
+    n = 5003
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for cin, cout in ((4, 8), (8, 16), (16, 32)):
+        assert ops.h2out_supported("k1", cin, cout)
+        f = torch.randn(n, cin, generator=g).to(DEV)
+        w = torch.randn(cin, cout, generator=g).to(DEV)
+        b = torch.randn(1, cout, generator=g).to(DEV)
+        res = torch.randn(n, cout, generator=g).to(DEV)
+        want = ops.conv_k1(f, w, b, residual=res, relu=True)
+        wide = torch.zeros((n, 2 * cout), device=DEV)
+        wide_h = torch.full((n, 2 * cout), 3, dtype=torch.int32, device=DEV)
+        got, got_h = ops.conv_k1(f, w, b, residual=res, relu=True, out=wide[:, cout:], out_h2=wide_h[:, cout:], overflow=flag)
+        assert torch.equal(got, want) and torch.equal(got_h, ops.split_h2(want)) and (wide_h[:, :cout] == 3).all()
+    assert not ops.h2out_supported("k1", 32, 8) and not ops.h2out_supported("k1", 64, 16)
+    c = _surface()[:6001]
+    keys, _ = ops.argsort_u64(_keys(c))
+    for cin, cout in ((16, 32), (32, 64), (64, 32)):
+        assert ops.h2out_supported("down", cin, cout)
+        pk, rows, off, _ = ops.stride_down(keys, keys_are_sorted=True, with_parent_of=True)
+        f = torch.randn(len(c), cin, generator=g).to(DEV)
+        w = (torch.randn(8, cin, cout, generator=g) / np.sqrt(8 * cin)).to(DEV)
+        b = torch.randn(1, cout, generator=g).to(DEV)
+        want = ops.conv_k2s2(f, keys, rows, off, w, b, relu=True)
+        got, got_h = ops.conv_k2s2(f, keys, rows, off, w, b, relu=True, out_h2=True, overflow=flag)
+        assert torch.equal(got, want) and torch.equal(got_h, ops.split_h2(want))
+    for cin, cout in ((64, 32), (32, 16)):
+        assert ops.h2out_supported("up", cin, cout)
+        f = torch.randn(1001, cin, generator=g).to(DEV)
+        w = (torch.randn(8, cin, cout, generator=g) / np.sqrt(cin)).to(DEV)
+        b = torch.randn(1, cout, generator=g).to(DEV)
+        want = ops.convT_k2s2(f, w, b, relu=True)
+        got, got_h = ops.convT_k2s2(f, w, b, relu=True, out_h2=True, overflow=flag)
+        assert torch.equal(got, want) and torch.equal(got_h, ops.split_h2(want))
+    assert int(flag.item()) == 0
+    ops.convT_k2s2(f * 1e6, w, b, out_h2=True, overflow=flag)
+    assert int(flag.item()) == 1
+
+
 def test_conv_k3_h2_overflow_flag_and_small_weights():
     """tiny weights keep their precision through the power-of-two scale; an output beyond the f16 range raises the flag."""
     c = _surface()[:4001]
