@@ -376,8 +376,15 @@ class Codec:
             buf = self._pinned[name] = torch.empty(max(n, 1) * 5 // 4 + 16, dtype=dtype, pin_memory=True)
         return buf[:n].view(shape)
 
-    @torch.no_grad()
     def _encode(self, coords, dedupe=False):
+        with torch.no_grad(), ops.stream_scope():
+            return self._encode_pass(coords, dedupe)
+
+    def _decode(self, stream: Stream, rho: float = 1.0, to_host: bool = True):
+        with torch.no_grad(), ops.stream_scope():
+            return self._decode_pass(stream, rho, to_host)
+
+    def _encode_pass(self, coords, dedupe=False):
         coords = torch.as_tensor(coords, dtype=torch.int32).to(self.device, non_blocking=True)   # async from pinned host memory
         if coords.shape[1] == 3:                                          # batch column added on the device
             coords = torch.nn.functional.pad(coords, (1, 0))
@@ -408,8 +415,7 @@ class Codec:
         return Stream(F=f_bytes, H=h_bytes, num_points=np.array(num_points, dtype=np.int32).tobytes(),
                       coords=c3_h.numpy().copy(), stats={"N": num_points, "sym_range": (lo, hi)})
 
-    @torch.no_grad()
-    def _decode(self, stream: Stream, rho: float = 1.0, to_host: bool = True):
+    def _decode_pass(self, stream: Stream, rho: float = 1.0, to_host: bool = True):
         shape = np.frombuffer(stream.H[:8], dtype=np.int32)
         lo = int(np.frombuffer(stream.H[9:13], dtype=np.float32)[0])
         hi = int(np.frombuffer(stream.H[13:17], dtype=np.float32)[0])

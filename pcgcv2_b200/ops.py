@@ -6,6 +6,8 @@ in ``torch.int64`` tensors holding the uint64 bit pattern described in pcgc.h.
 """
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 import torch
 
@@ -20,8 +22,26 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+_TLS = threading.local()   # .stream: raw handle of the thread's current stream, looked up once per pipeline pass (stream_scope)
+
+
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    h = getattr(_TLS, "stream", None)
+    return h if h is not None else torch.cuda.current_stream().cuda_stream
+
+
+class stream_scope:
+    """with ops.stream_scope(): ... -- every operator this thread calls inside launches on the stream that is current on
+    entry without asking torch for it again (about 2 us per launch); do not switch streams inside."""
+
+    def __enter__(self):
+        self.prev = getattr(_TLS, "stream", None)
+        _TLS.stream = torch.cuda.current_stream().cuda_stream
+        return self
+
+    def __exit__(self, *exc):
+        _TLS.stream = self.prev
+        return False
 
 
 def _need_cuda(*ts):
@@ -336,8 +356,14 @@ def conv_k3_h2(feats_h2, nbr, pw: PackedK3H2, bias=None, residual=None, relu=Fal
     return out, out_h2
 
 
+_SUPPORT = {}
+
+
 def octet_h2_supported(cin, cout) -> bool:
-    return bool(_lib.lib().pcgc_conv_k3_octet_h2_supported(int(cin), int(cout)))
+    key = ("octet_h2", int(cin), int(cout))
+    if key not in _SUPPORT:
+        _SUPPORT[key] = bool(_lib.lib().pcgc_conv_k3_octet_h2_supported(int(cin), int(cout)))
+    return _SUPPORT[key]
 
 
 def conv_k3_octet_h2(feats_h2, parent_nbr, pw: PackedK3H2, bias=None, residual=None, relu=False, out=None, out_h2=None,
@@ -364,7 +390,10 @@ def conv_k3_octet_h2(feats_h2, parent_nbr, pw: PackedK3H2, bias=None, residual=N
 
 def h2out_supported(kind: str, cin, cout) -> bool:
     """kind in {"k1", "down", "up"}: the layer's kernel can write the h2 copy of its output in its epilogue."""
-    return bool(_lib.lib().pcgc_conv_h2out_supported({"k1": 1, "down": 2, "up": 3}[kind], int(cin), int(cout)))
+    key = (kind, int(cin), int(cout))
+    if key not in _SUPPORT:
+        _SUPPORT[key] = bool(_lib.lib().pcgc_conv_h2out_supported({"k1": 1, "down": 2, "up": 3}[kind], int(cin), int(cout)))
+    return _SUPPORT[key]
 
 
 def _h2_out(out_h2, n, cout, device):

@@ -192,3 +192,27 @@ def test_h2_path_equals_tf32_path_and_falls_back_on_overflow(r3):
     fast, slow = Codec(big), Codec(big, use_h2=False)
     got, want = fast.decode(a), slow.decode(b)
     assert fast.h2_fallbacks >= 1 and (canon(got) == canon(want)).all()
+
+
+def test_frame_pipeline_matches_single_frame_path(r3):
+    """several frames in flight (one host thread + CUDA stream each) == the same frames one at a time."""
+    from pcgcv2_b200.pipeline import FramePipeline
+    frames = [synth.ellipsoid_vox8(), synth.random_cube(1, 32, 0.1), synth.random_cube(2, 48, 0.05), synth.ellipsoid_vox8(),
+              synth.random_cube(3, 32, 0.2)]
+    single = Codec(r3)
+    want = []
+    for f in frames:
+        st = single.encode(f)
+        want.append((st, single.decode(st).copy()))
+    with FramePipeline(r3, depth=2) as pipe:
+        for _ in range(2):                                        # twice: staging buffers are reused across calls
+            got = pipe.roundtrip(frames)
+            assert len(got) == len(frames)
+            for (st, dec), (st_w, dec_w) in zip(got, want):
+                assert st.F == st_w.F and st.H == st_w.H and st.num_points == st_w.num_points and (st.coords == st_w.coords).all()
+                assert (canon(dec) == canon(dec_w)).all()
+        dev = pipe.roundtrip([torch.from_numpy(frames[0]).cuda()], to_host=False)[0][1]
+        assert dev.is_cuda and (canon(dev.cpu().numpy()) == canon(want[0][1])).all()
+        with pytest.raises(Exception):
+            pipe.roundtrip([np.zeros((4, 2), dtype=np.int32)])    # a worker's error reaches the caller
+        assert len(pipe.roundtrip(frames[:1])) == 1               # and the pipeline stays usable
