@@ -184,7 +184,8 @@ int pcgc_conv_k3_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *nbr
                         int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld,
                         int32_t flags, int32_t *overflow, void *stream);
 /* a3 on FULL-OCTET sets over h2 features: the halo staging of pcgc_conv_k3_octet_fwd feeding the f16 arithmetic of
- * pcgc_conv_k3_h2_fwd (same packed weights and scale as the latter).  cin = 16, cout in {1,4,8,16,32}. */
+ * pcgc_conv_k3_h2_fwd (same packed weights and scale as the latter).  cin = 16, cout in {1,4,8,16,32}; and cin = 4,
+ * cout in {4,8} (full-octet only: one MMA carries hi*Whi + lo*Whi + hi*Wlo of a 4-channel row). */
 int pcgc_conv_k3_octet_h2_supported(int32_t cin, int32_t cout);
 int pcgc_conv_k3_octet_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *parent_nbr, int64_t n_parents,
                               const uint32_t *packed, float inv_scale, const float *bias, int32_t cin, int32_t cout,

@@ -156,6 +156,8 @@ class Codec:
         aligned = x.f is None or x.f.stride(0) % 4 == 0
         ph = self.packed_h2.get(name) if self._h2_on else None
         oh = ph if (ph is not None and level.full_octets and self.use_octet and ops.octet_h2_supported(ph.cin, ph.cout)) else None
+        if ph is not None and oh is None and not ph.gather:
+            ph = None
         po = self.packed_octet.get(name) if (oh is None and level.full_octets and aligned and x.f is not None) else None
         if po is not None:
             ph = None
@@ -216,10 +218,12 @@ class Codec:
             return True
         if not (self._h2_on and name in self.packed_h2):
             return False
+        ph = self.packed_h2[name]
+        if level.full_octets and self.use_octet and ops.octet_h2_supported(ph.cin, ph.cout):
+            return True
         if level.full_octets and name in self.packed_octet:
-            ph = self.packed_h2[name]
-            return self.use_octet and ops.octet_h2_supported(ph.cin, ph.cout)
-        return True
+            return False
+        return ph.gather
 
     def _irn(self, prefix, x: _F, level) -> _F:
         """InceptionResNet (autoencoder.py:52-57) as 5 fused launches: the two branch outputs are

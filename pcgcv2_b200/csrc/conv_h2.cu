@@ -96,7 +96,31 @@ static int launch_octet_h2(const uint32_t *in, int in_ld, const int32_t *pnbr, i
     }
 }
 
-static bool octet_h2_shape(int cin, int cout) { return cin == 16 && (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32); }
+template <int COUT>
+static int launch_octet_h2c4(const uint32_t *in, int in_ld, const int32_t *pnbr, int64_t n_par, const uint32_t *packed, float inv_scale,
+                             const float *bias, const float *res, int res_ld, float *out, int out_ld, uint32_t *out_h2,
+                             int out_h2_ld, int flags, int *overflow, cudaStream_t s) {
+    constexpr int RG = 2, WARPS = 8, MINB = 2;
+    using C = OctetH2C4Cfg<COUT, RG, WARPS>;
+    auto kern = conv_k3_octet_h2c4_kernel<COUT, RG, WARPS, MINB>;
+    static int ctas = 0;
+    if (ctas == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
+        if (e != cudaSuccess) { set_error("octet h2 conv 4x%d: %s", COUT, cudaGetErrorString(e)); return PCGC_ERR_CUDA; }
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, C::smem_bytes()) != cudaSuccess || nb < 1) nb = 1;
+        ctas = nb;
+    }
+    kern<<<grid_for(n_par, C::OCTETS_PER_CTA, ctas), C::THREADS, C::smem_bytes(), s>>>(in, in_ld, pnbr, n_par, packed, inv_scale, bias,
+                                                                                     res, res_ld, out, out_ld, out_h2, out_h2_ld,
+                                                                                     flags, overflow);
+    return check_launch("conv_k3_octet_h2c4");
+}
+
+static bool octet_h2c4_shape(int cin, int cout) { return cin == 4 && (cout == 4 || cout == 8); }
+static bool octet_h2_shape(int cin, int cout) {
+    return (cin == 16 && (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32)) || octet_h2c4_shape(cin, cout);
+}
 
 static bool h2_shape(int cin, int cout) {
     if (cin == 16) return cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32;
@@ -132,6 +156,7 @@ int pcgc_join_h2(const uint32_t *in_h2, int32_t in_ld, int64_t n, int32_t c, flo
 }
 
 size_t pcgc_conv_k3_h2_packed_words(int32_t cin, int32_t cout) {
+    if (octet_h2c4_shape(cin, cout)) return (size_t)27 * ((cout + 7) / 8) * 64;      // full-octet kernel only
     if (!h2_shape(cin, cout)) return 0;
     return cout < 16 ? (size_t)27 * (cin / 16) * ((cout + 7) / 8) * 128 : (size_t)27 * (cin / 16) * (cout / 16) * 256;
 }
@@ -140,6 +165,10 @@ int pcgc_conv_k3_h2_pack_weights(const float *weight, int32_t cin, int32_t cout,
     const size_t total = pcgc_conv_k3_h2_packed_words(cin, cout);
     PCGC_REQUIRE(total > 0 && weight && packed, "pcgc_conv_k3_h2_pack_weights: no h2 kernel for %dx%d", cin, cout);
     PCGC_REQUIRE(scale > 0.f, "pcgc_conv_k3_h2_pack_weights: scale must be positive");
+    if (octet_h2c4_shape(cin, cout)) {
+        pack_weights_h2c4_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(weight, cout, scale, packed);
+        return check_launch("pack_weights_h2c4");
+    }
     pack_weights_h2_kernel<<<grid_for((int64_t)total / 2, 256, 4), 256, 0, (cudaStream_t)stream>>>(weight, 27, cin, cout, cout < 16 ? 1 : 0,
                                                                                                 scale, packed);
     return check_launch("pack_weights_h2");
@@ -153,7 +182,7 @@ int pcgc_conv_k3_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *nbr
                  (long long)n, cin, cout, in_ld);
     if (n == 0) return PCGC_OK;
     PCGC_REQUIRE(in_h2 && nbr && packed && (out || out_h2), "pcgc_conv_k3_h2_fwd: null pointer");
-    PCGC_REQUIRE(pcgc_conv_k3_h2_packed_words(cin, cout) > 0, "pcgc_conv_k3_h2_fwd: no h2 kernel for %dx%d", cin, cout);
+    PCGC_REQUIRE(h2_shape(cin, cout), "pcgc_conv_k3_h2_fwd: no gather h2 kernel for %dx%d", cin, cout);
     PCGC_REQUIRE((in_ld % 4 == 0) && (((uintptr_t)in_h2 & 15) == 0) && (((uintptr_t)packed & 15) == 0),
                  "pcgc_conv_k3_h2_fwd: input rows must be 16-byte aligned (ld %% 4 == 0)");
     if (cout % 2 == 0) {
@@ -199,6 +228,8 @@ int pcgc_conv_k3_octet_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_
     if (cin == CI && cout == CO) return launch_octet_h2<CI, CO>(in_h2, in_ld, parent_nbr, n_parents, packed, inv_scale, bias, residual, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
     OH2(16, 1) OH2(16, 4) OH2(16, 8) OH2(16, 16) OH2(16, 32)
 #undef OH2
+    if (cin == 4 && cout == 8) return launch_octet_h2c4<8>(in_h2, in_ld, parent_nbr, n_parents, packed, inv_scale, bias, residual, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
+    if (cin == 4 && cout == 4) return launch_octet_h2c4<4>(in_h2, in_ld, parent_nbr, n_parents, packed, inv_scale, bias, residual, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
     set_error("pcgc_conv_k3_octet_h2_fwd: shape %dx%d has no instantiation", cin, cout);
     return PCGC_ERR_INVALID;
 }

@@ -193,4 +193,135 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
     if (epi.over && overflow) *overflow = 1;
 }
 
+// ---- CIN = 4 (the 4 -> 8 and 4 -> 4 layers of the finest InceptionResNet blocks) ----------------------------------
+// An h2 row of four channels is exactly one 16-byte group {hi01 hi23 lo01 lo23}.  All three products of the split
+// arithmetic fit ONE m16n8k16 MMA: the sixteen contraction slots carry [hi01 hi23 lo01 lo23 | hi01 hi23 0 0] on the
+// feature side and [Whi01 Whi23 Whi01 Whi23 | Wlo01 Wlo23 0 0] on the weight side, i.e. hi*Whi + lo*Whi + hi*Wlo.
+// Lane (g, t) supplies slot t (the t-th 32-bit word of its row: one LDS.32, bank-conflict free) and slot t + 4 (the
+// same word again for t < 2, zero otherwise).  One accumulator chain per kernel z-plane (9 MMAs), joined by RN FADDs.
+template <int COUT, int RG_, int WARPS_>
+struct OctetH2C4Cfg {
+    static_assert(COUT == 4 || COUT == 8 || COUT == 16, "octet h2 CIN=4 kernel: COUT in {4, 8, 16}");
+    static constexpr int CT = (COUT + 7) / 8;
+    static constexpr int RG = RG_, WARPS = WARPS_, THREADS = 32 * WARPS_;
+    static constexpr int OW = 2 * RG;                              // octets per warp iteration (16 rows per group)
+    static constexpr int SY = 4, SZ = 18;                          // rows {0,1,4,5,18,19,22,23} x 4 words: 32 distinct banks
+    static constexpr int HROWS = 3 * SZ + 3 * SY + 4;
+    static constexpr int HB = HROWS * 16;
+    static constexpr int W_OFF = CT * 64;                          // packed words per offset: [CT][32 lanes][2]
+    static constexpr size_t packed_words() { return (size_t)27 * W_OFF; }
+    static constexpr size_t weight_bytes() { return (packed_words() * 4 + 127) / 128 * 128; }
+    static constexpr size_t warp_bytes() { return ((size_t)OW * HB + (size_t)27 * OW * 4 + 127) / 128 * 128; }
+    static constexpr size_t smem_bytes() { return weight_bytes() + (size_t)WARPS * warp_bytes(); }
+    static constexpr int OCTETS_PER_CTA = WARPS * OW;
+};
+
+// W [27][4][cout] -> [27][CT][32 lanes] x {b0, b1}: b0 = slot t: (t & 1 ? Whi[2,3] : Whi[0,1])[8c+g], b1 = slot t+4: Wlo (t < 2) or 0
+static __global__ void pack_weights_h2c4_kernel(const float *__restrict__ w, int cout, float scale, uint32_t *__restrict__ packed) {
+    const int CT = (cout + 7) / 8;
+    const int total = 27 * CT * 32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int lane = i & 31, c = (i >> 5) % CT, k = (i >> 5) / CT;
+        const int g = lane >> 2, t = lane & 3, co = 8 * c + g, ci = 2 * (t & 1);
+        const float x0 = co < cout ? w[(k * 4 + ci) * cout + co] * scale : 0.f;
+        const float x1 = co < cout ? w[(k * 4 + ci + 1) * cout + co] * scale : 0.f;
+        uint32_t hi, lo;
+        split_pair_h2(x0, x1, hi, lo);
+        packed[2 * i] = hi;
+        packed[2 * i + 1] = t < 2 ? lo : 0u;
+    }
+}
+
+template <int COUT, int RG, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+conv_k3_octet_h2c4_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__restrict__ pnbr, int64_t n_par,
+                          const uint32_t *__restrict__ packed, float inv_scale, const float *__restrict__ bias,
+                          const float *__restrict__ residual, int res_ld, float *__restrict__ out, int out_ld,
+                          uint32_t *__restrict__ out_h2, int out_h2_ld, int flags, int *__restrict__ overflow) {
+    using C = OctetH2C4Cfg<COUT, RG, WARPS>;
+    constexpr int CT = C::CT, OW = C::OW, SY = C::SY, SZ = C::SZ, HB = C::HB, W_OFF = C::W_OFF;
+    extern __shared__ __align__(128) unsigned char smem_oh2[];
+    uint32_t *wsm = reinterpret_cast<uint32_t *>(smem_oh2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    unsigned char *halo = smem_oh2 + C::weight_bytes() + (size_t)warp * C::warp_bytes();
+    int32_t *sidx = reinterpret_cast<int32_t *>(halo + (size_t)OW * HB);
+
+    for (int i = threadIdx.x; i < (int)C::packed_words(); i += C::THREADS) wsm[i] = __ldg(packed + i);
+    __syncthreads();
+
+    const int cx = g & 1, cy = (g >> 1) & 1, cz = g >> 2;
+    const unsigned char *base = halo + (cx + SY * cy + SZ * cz) * 16 + 4 * t;       // child g, word t of the row
+    const bool dup = t < 2;                                                         // slots 4, 5 repeat the hi words
+
+    const int64_t n_tiles = (n_par + C::OCTETS_PER_CTA - 1) / C::OCTETS_PER_CTA;
+    const char *in_bytes = reinterpret_cast<const char *>(in);
+    const uint32_t ldb = (uint32_t)in_ld * 4u;
+    H2Epilogue epi{bias, residual, out, out_h2, res_ld, out_ld, out_h2_ld, flags, inv_scale};
+    int32_t prow[OW];
+    load_parent_rows<OW>(prow, pnbr, n_par, (int64_t)blockIdx.x * C::OCTETS_PER_CTA + warp * OW, lane);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t oct0 = tile * C::OCTETS_PER_CTA + warp * OW;
+        __syncwarp();
+        store_parent_rows<OW>(sidx, prow, lane);
+        __syncwarp();
+        halo_fill<1, OW, HB, 16, SY, SZ, false>(halo, sidx, in_bytes, ldb, lane);
+        load_parent_rows<OW>(prow, pnbr, n_par, (tile + gridDim.x) * C::OCTETS_PER_CTA + warp * OW, lane);
+
+        float acc[CT][RG][4];
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+#pragma unroll
+            for (int r = 0; r < RG; ++r)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[c][r][e] = 0.f;
+
+#pragma unroll
+        for (int iz = 0; iz < 3; ++iz) {
+            halo_wait(iz);
+            float plane[CT][RG][4];
+#pragma unroll
+            for (int oo = 0; oo < 9; ++oo) {
+                const int o = 9 * iz + oo, ix = oo % 3, iy = oo / 3;
+                const int doff = (ix + SY * iy + SZ * iz) * 16;
+                uint2 w[CT];
+#pragma unroll
+                for (int c = 0; c < CT; ++c) w[c] = *reinterpret_cast<const uint2 *>(wsm + o * W_OFF + (c * 32 + lane) * 2);
+#pragma unroll
+                for (int r = 0; r < RG; ++r) {
+                    const uint32_t a0 = *reinterpret_cast<const uint32_t *>(base + (2 * r) * HB + doff);
+                    const uint32_t a1 = *reinterpret_cast<const uint32_t *>(base + (2 * r + 1) * HB + doff);
+                    const uint32_t a2 = dup ? a0 : 0u, a3 = dup ? a1 : 0u;
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) {
+                        if (oo == 0) mma_f16_zero(plane[c][r], a0, a1, a2, a3, w[c].x, w[c].y);
+                        else mma_f16(plane[c][r], a0, a1, a2, a3, w[c].x, w[c].y);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+#pragma unroll
+                for (int r = 0; r < RG; ++r)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[c][r][e] += plane[c][r][e];
+        }
+
+        const int64_t n = n_par * 8, row0 = oct0 * 8;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const int co = 8 * c + 2 * t;
+            if (co >= COUT) continue;
+#pragma unroll
+            for (int r = 0; r < RG; ++r)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t row = row0 + 16 * r + 8 * h + g;
+                    if (row >= n) continue;
+                    epi.store_pair(row, co, acc[c][r][2 * h], acc[c][r][2 * h + 1]);
+                }
+        }
+    }
+    if (epi.over && overflow) *overflow = 1;
+}
+
 }  // namespace pcgc

@@ -321,6 +321,11 @@ class PackedK3H2:
     def supported(cin, cout) -> bool:
         return int(_lib.lib().pcgc_conv_k3_h2_packed_words(int(cin), int(cout))) > 0
 
+    @property
+    def gather(self) -> bool:
+        """a child-map (gather) kernel exists for the shape; cin = 4 has the full-octet kernel only."""
+        return self.cin % 16 == 0
+
     def __init__(self, weight: torch.Tensor):
         assert weight.dim() == 3 and weight.shape[0] == 27 and weight.is_contiguous()
         self.cin, self.cout = int(weight.shape[1]), int(weight.shape[2])

@@ -376,10 +376,10 @@ def test_conv_k3_h2_vs_oracle(cin, cout):
         assert _rel_err(got, torch.relu(S.conv_k3(f[:n], cc, 1, w, b))) < H2_TOL
 
 
-@pytest.mark.parametrize("cout", [1, 4, 8, 16, 32])
-def test_conv_k3_octet_h2_vs_oracle(cout):
-    """full-octet h2 kernels (halo of h2 rows in shared memory, parent's map) == oracle on the 8-child expansion."""
-    cin = 16
+@pytest.mark.parametrize("cin,cout", [(16, 1), (16, 4), (16, 8), (16, 16), (16, 32), (4, 8), (4, 4)])
+def test_conv_k3_octet_h2_vs_oracle(cin, cout):
+    """full-octet h2 kernels (halo of h2 rows in shared memory, parent's map) == oracle on the 8-child expansion;
+    cin = 4: all three split products in one MMA."""
     par = _surface()[:6007]
     par[:, 1:] *= 2
     pkeys, _ = ops.argsort_u64(_keys(par, 2))
