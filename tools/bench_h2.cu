@@ -119,6 +119,21 @@ int main(int argc, char **argv) {
     std::vector<int32_t> h(27 * n);
     if (fread(h.data(), 4, 27 * n, f) != (size_t)(27 * n)) return 1;
     fclose(f);
+    if (argc > 2) {                                  // row limit: the first `limit` rows of the map as a smaller level
+        const int64_t limit = atoll(argv[2]);
+        if (limit > 0 && limit < n) {
+            std::vector<int32_t> h2(27 * limit);
+            pairs = 0;
+            for (int k = 0; k < 27; ++k)
+                for (int64_t r = 0; r < limit; ++r) {
+                    const int32_t v = h[k * n + r];
+                    h2[k * limit + r] = (v >= 0 && v < limit) ? v : -1;
+                    pairs += h2[k * limit + r] >= 0;
+                }
+            h.swap(h2);
+            n = limit;
+        }
+    }
     printf("rows %lld pairs %lld\n", (long long)n, (long long)pairs);
     g_n = n; g_pairs = pairs;
     int32_t *nbr; CK(cudaMalloc(&nbr, 27 * n * 4)); CK(cudaMemcpy(nbr, h.data(), 27 * n * 4, cudaMemcpyHostToDevice));
