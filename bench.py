@@ -205,7 +205,7 @@ def run_ours(args, rank, world, local_rank):
                    "points_per_frame": n0, "frames_per_step": world * depth,
                    "parallelism": f"frames sharded over {world} GPU(s), {depth} frame(s) in flight per GPU (one host thread + "
                                   "CUDA stream each: the host range coder of one frame overlaps the kernels of the other)",
-                   "serial_ms_per_frame": round(ms_serial / args.steps, 3),
+                   "serial_ms_per_frame": round(ms_serial / args.steps, 3), "host_cpus": len(os.sched_getaffinity(0)),
                    "bpp_features": round(total_bits / total_pts, 5),
                    "coords_side_channel": "raw int32 hand-over (tmc3 subprocess out of scope)",
                    "l2": "per-step traffic (~8.6 GB algorithmic, >1 GB live) exceeds the 126 MB L2; no flush needed"},

@@ -191,6 +191,26 @@ int pcgc_conv_k3_octet_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_
                               const uint32_t *packed, float inv_scale, const float *bias, int32_t cin, int32_t cout,
                               const float *residual, int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2,
                               int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream);
+/* a5 / a6 on the tensor cores over h2 features.
+ * k=2 stride 2 (a5): the h2 gather kernel over the 8 child slots of every parent.  child_map int32 [8][n_parents]:
+ * child_map[k][p] = input row of child k = in_key & 7 of parent p, or -1.  Shapes 16x32, 32x64, 64x32.
+ * Transposed k=2 stride 2 (a6): ONE dense product [n_in, cin] x [cin, 8*cout] -- the [8*n_in, cout] child tensor is
+ * the same memory as [n_in, 8*cout], so out / out_h2 must be contiguous (ld == cout).  bias8 = the bias repeated 8
+ * times (8*cout floats).  pack_weights needs a float workspace of 8*cin*cout for the re-ordered kernel.
+ * cin in {16,32,64}, cout <= 64. */
+size_t pcgc_conv_k2s2_h2_packed_words(int32_t cin, int32_t cout);
+int pcgc_conv_k2s2_h2_pack_weights(const float *weight, int32_t cin, int32_t cout, float scale, uint32_t *packed,
+                                   void *stream);
+int pcgc_conv_k2s2_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *child_map, int64_t n_parents,
+                          const uint32_t *packed, float inv_scale, const float *bias, int32_t cin, int32_t cout,
+                          float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t flags,
+                          int32_t *overflow, void *stream);
+size_t pcgc_convT_k2s2_h2_packed_words(int32_t cin, int32_t cout);
+int pcgc_convT_k2s2_h2_pack_weights(const float *weight, int32_t cin, int32_t cout, float scale, float *dense_ws,
+                                    uint32_t *packed, void *stream);
+int pcgc_convT_k2s2_h2_fwd(const uint32_t *in_h2, int32_t in_ld, int64_t n_in, const uint32_t *packed, float inv_scale,
+                           const float *bias8, int32_t cin, int32_t cout, float *out, int32_t out_ld,
+                           uint32_t *out_h2, int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream);
 /* a7  ME.MinkowskiConvolution(kernel_size=1) == F.mm(kernel) + bias. */
 int pcgc_conv_k1_fwd(const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias,
                      int32_t cin, int32_t cout, const float *residual, int32_t res_ld, float *out,

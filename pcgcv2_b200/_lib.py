@@ -66,6 +66,14 @@ SIGNATURES = {
     "pcgc_conv_k3_octet_h2_supported": (ctypes.c_int, [c_i32, c_i32]),
     "pcgc_conv_k3_octet_h2_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, ctypes.c_float, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32,
                                                   c_p, c_i32, c_i32, c_p, c_p]),
+    "pcgc_conv_k2s2_h2_packed_words": (c_sz, [c_i32, c_i32]),
+    "pcgc_conv_k2s2_h2_pack_weights": (ctypes.c_int, [c_p, c_i32, c_i32, ctypes.c_float, c_p, c_p]),
+    "pcgc_conv_k2s2_h2_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, ctypes.c_float, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32,
+                                              c_i32, c_p, c_p]),
+    "pcgc_convT_k2s2_h2_packed_words": (c_sz, [c_i32, c_i32]),
+    "pcgc_convT_k2s2_h2_pack_weights": (ctypes.c_int, [c_p, c_i32, c_i32, ctypes.c_float, c_p, c_p, c_p]),
+    "pcgc_convT_k2s2_h2_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, ctypes.c_float, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32,
+                                               c_p, c_p]),
     "pcgc_conv_k1_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),
     "pcgc_conv_k2s2_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_i32, c_p]),
     "pcgc_convT_k2s2_fwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_i32, c_p]),

@@ -126,6 +126,15 @@ class Codec:
                         and v.shape[2] % 16 == 0 and ops.PackedK3H2.supported(v.shape[1], 16)):
                     self.packed_h2_slices[name] = [(ops.PackedK3H2(v[:, :, j:j + 16].contiguous()),
                                                     self.w[name + ".bias"][:, j:j + 16]) for j in range(0, v.shape[2], 16)]
+        # k=2 stride-2 / transposed layers on the tensor cores (gather over the 8 child slots / one dense product)
+        self.packed_down_h2, self.packed_up_h2 = {}, {}
+        if use_h2 and use_tensor_cores:
+            for k, v in self.w.items():
+                name = k[:-len(".kernel")]
+                if k.endswith(".kernel") and v.dim() == 3 and v.shape[0] == 8:
+                    pw = ops.PackedDownH2(v) if ".down" in name else ops.PackedUpH2(v, self.w.get(name + ".bias"))
+                    if pw.packed is not None:
+                        (self.packed_down_h2 if ".down" in name else self.packed_up_h2)[name] = pw
         self._h2_on = bool(self.packed_h2)
         self.use_octet = use_octet_kernels
         self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)   # raised by an h2 producer: re-run in fp32
@@ -286,7 +295,12 @@ class Codec:
         for i in range(3):
             rows, off = down[i]
             wd = self.w[f"encoder.down{i}.kernel"]
-            if self._h2_on and ops.h2out_supported("down", wd.shape[1], wd.shape[2]):    # the IRN's h2 layers read this
+            pd = self.packed_down_h2.get(f"encoder.down{i}") if self._h2_on else None
+            if pd is not None:                                                           # tensor cores over the 8 child slots
+                cmap = ops.child_map_k2(level.keys, level.parent_of, len(levels[i + 1]))
+                x = _F(*ops.conv_k2s2_h2(self._h(x), cmap, pd, self.w[f"encoder.down{i}.bias"], relu=True,
+                                         want_f32=True, want_h2=True, overflow=self._overflow))
+            elif self._h2_on and ops.h2out_supported("down", wd.shape[1], wd.shape[2]):  # the IRN's h2 layers read this
                 x = _F(*ops.conv_k2s2(x.f, level.keys, rows, off, wd, self.w[f"encoder.down{i}.bias"], relu=True, out_h2=True,
                                       overflow=self._overflow))
             else:
@@ -296,7 +310,8 @@ class Codec:
             for j in range(3):
                 x = self._irn(f"encoder.block{i}.{j}", x, level)
             sizes.append(len(level))
-            x = self._k3(f"encoder.conv{i + 1}", x, level, relu=(i < 2))
+            x = self._k3(f"encoder.conv{i + 1}", x, level, relu=(i < 2),
+                         want_h=i < 2 and self._h2_on and f"encoder.down{i + 1}" in self.packed_down_h2)
         return x.f, level, [sizes[2], sizes[1], sizes[0]]
 
     def synthesis(self, y: torch.Tensor, level: _Level, nums):
@@ -304,7 +319,11 @@ class Codec:
         x, cls_list = y, []
         for i in range(3):
             wu = self.w[f"decoder.up{i}.kernel"]
-            if self._h2_on and self._uses_h2(f"decoder.conv{i}", _FULL) and ops.h2out_supported("up", wu.shape[1], wu.shape[2]):
+            pu = self.packed_up_h2.get(f"decoder.up{i}") if (self._h2_on and self._uses_h2(f"decoder.conv{i}", _FULL)) else None
+            if pu is not None:                               # one dense tensor-core product; only the h2 copy is consumed
+                x = _F(*ops.convT_k2s2_h2(ops.split_h2(x, overflow=self._overflow), pu, relu=True,
+                                          want_f32=self.record is not None, want_h2=True, overflow=self._overflow))
+            elif self._h2_on and self._uses_h2(f"decoder.conv{i}", _FULL) and ops.h2out_supported("up", wu.shape[1], wu.shape[2]):
                 x = _F(*ops.convT_k2s2(x, wu, self.w[f"decoder.up{i}.bias"], relu=True, out_h2=True, overflow=self._overflow))
             else:
                 x = _F(ops.convT_k2s2(x, wu, self.w[f"decoder.up{i}.bias"], relu=True))

@@ -122,6 +122,52 @@ static bool octet_h2_shape(int cin, int cout) {
     return (cin == 16 && (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32)) || octet_h2c4_shape(cin, cout);
 }
 
+// k=2 stride-2 convolution = the gather kernel over the 8 child slots of every parent (KV = 8, T formulation)
+template <int CIN, int COUT>
+static int launch_down_h2(const uint32_t *in, int in_ld, const int32_t *child_map, int64_t n_par, const uint32_t *packed,
+                          float inv_scale, const float *bias, float *out, int out_ld, uint32_t *out_h2, int out_h2_ld, int flags,
+                          int *overflow, cudaStream_t s) {
+    constexpr int RG = 2, D = CIN == 64 ? 1 : 2, WARPS = 8, MINB = CIN == 64 ? 1 : 2;
+    using C = H2Cfg<CIN, COUT, false, RG, D, WARPS, 8>;
+    auto kern = conv_k3_h2_kernel<CIN, COUT, false, RG, D, WARPS, MINB, 8>;
+    static int ctas = 0;
+    if (ctas == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
+        if (e != cudaSuccess) { set_error("h2 k2s2 conv %dx%d: %s", CIN, COUT, cudaGetErrorString(e)); return PCGC_ERR_CUDA; }
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, C::smem_bytes()) != cudaSuccess || nb < 1) nb = 1;
+        ctas = nb;
+    }
+    kern<<<grid_for(n_par, C::ROWS_PER_CTA, ctas), C::THREADS, C::smem_bytes(), s>>>(in, in_ld, child_map, n_par, packed, inv_scale, bias,
+                                                                                   nullptr, 0, out, out_ld, out_h2, out_h2_ld, flags,
+                                                                                   overflow);
+    return check_launch("conv_k2s2_h2");
+}
+
+template <int CIN>
+static int launch_dense_h2(const uint32_t *in, int in_ld, int64_t n, const uint32_t *packed, int nc, float inv_scale,
+                           const float *bias, float *out, int out_ld, uint32_t *out_h2, int out_h2_ld, int flags, int *overflow,
+                           cudaStream_t s) {
+    constexpr int RG = 2, WARPS = 8, MINB = 2;
+    using C = DenseH2Cfg<CIN, RG, WARPS>;
+    auto kern = dense_h2_kernel<CIN, RG, WARPS, MINB>;
+    const size_t smem = C::smem_bytes(nc);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("dense h2 %dx%d: %s", CIN, nc, cudaGetErrorString(e)); return PCGC_ERR_CUDA; }
+        smem_set = smem;
+    }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+    kern<<<grid_for(n, C::ROWS_PER_CTA, nb), C::THREADS, smem, s>>>(in, in_ld, n, packed, nc, inv_scale, bias, out, out_ld, out_h2,
+                                                                   out_h2_ld, flags, overflow);
+    return check_launch("dense_h2");
+}
+
+static bool down_h2_shape(int cin, int cout) { return (cin == 16 && cout == 32) || (cin == 32 && cout == 64) || (cin == 64 && cout == 32); }
+static bool up_h2_shape(int cin, int cout) { return (cin == 16 || cin == 32 || cin == 64) && cout % 2 == 0 && 8 * cout <= 512 && (8 * cout) % 16 == 0; }
+
 static bool h2_shape(int cin, int cout) {
     if (cin == 16) return cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32;
     if (cin == 32) return cout == 1 || cout == 4 || cout == 8 || cout == 32;
@@ -200,6 +246,78 @@ int pcgc_conv_k3_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *nbr
 #undef H2
     set_error("pcgc_conv_k3_h2_fwd: shape %dx%d has no instantiation", cin, cout);
     return PCGC_ERR_INVALID;
+}
+
+// ---- k=2 stride-2 (a5) and its generative transpose (a6) on the tensor cores over h2 features
+size_t pcgc_conv_k2s2_h2_packed_words(int32_t cin, int32_t cout) {
+    return down_h2_shape(cin, cout) ? (size_t)8 * (cin / 16) * (cout / 16) * 256 : 0;
+}
+
+int pcgc_conv_k2s2_h2_pack_weights(const float *weight, int32_t cin, int32_t cout, float scale, uint32_t *packed, void *stream) {
+    const size_t total = pcgc_conv_k2s2_h2_packed_words(cin, cout);
+    PCGC_REQUIRE(total > 0 && weight && packed && scale > 0.f, "pcgc_conv_k2s2_h2_pack_weights: no h2 kernel for %dx%d", cin, cout);
+    pack_weights_h2_kernel<<<grid_for((int64_t)total / 2, 256, 4), 256, 0, (cudaStream_t)stream>>>(weight, 8, cin, cout, 0, scale, packed);
+    return check_launch("pack_weights_h2");
+}
+
+int pcgc_conv_k2s2_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *child_map, int64_t n_parents,
+                          const uint32_t *packed, float inv_scale, const float *bias, int32_t cin, int32_t cout, float *out,
+                          int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream) {
+    PCGC_REQUIRE(n_parents >= 0 && down_h2_shape(cin, cout) && in_ld >= cin, "pcgc_conv_k2s2_h2_fwd: bad shape n=%lld %dx%d",
+                 (long long)n_parents, cin, cout);
+    if (n_parents == 0) return PCGC_OK;
+    PCGC_REQUIRE(in_h2 && child_map && packed && (out || out_h2), "pcgc_conv_k2s2_h2_fwd: null pointer");
+    PCGC_REQUIRE((in_ld % 4 == 0) && (((uintptr_t)in_h2 & 15) == 0) && (((uintptr_t)packed & 15) == 0),
+                 "pcgc_conv_k2s2_h2_fwd: input rows must be 16-byte aligned");
+    PCGC_REQUIRE(!out || (out_ld >= cout && out_ld % 2 == 0 && ((uintptr_t)out & 7) == 0), "pcgc_conv_k2s2_h2_fwd: out must be 8-byte aligned");
+    PCGC_REQUIRE(!out_h2 || (out_h2_ld >= cout && out_h2_ld % 4 == 0 && ((uintptr_t)out_h2 & 15) == 0),
+                 "pcgc_conv_k2s2_h2_fwd: h2 output rows must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cin == 16) return launch_down_h2<16, 32>(in_h2, in_ld, child_map, n_parents, packed, inv_scale, bias, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
+    if (cin == 32) return launch_down_h2<32, 64>(in_h2, in_ld, child_map, n_parents, packed, inv_scale, bias, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
+    return launch_down_h2<64, 32>(in_h2, in_ld, child_map, n_parents, packed, inv_scale, bias, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
+}
+
+size_t pcgc_convT_k2s2_h2_packed_words(int32_t cin, int32_t cout) {
+    return up_h2_shape(cin, cout) ? (size_t)(cin / 16) * (8 * cout / 16) * 256 : 0;
+}
+
+// weight [8][cin][cout] -> the dense [cin][8 * cout] operand (column k * cout + co), split and packed
+static __global__ void gather_up_weights_kernel(const float *__restrict__ w, int cin, int cout, float *__restrict__ dense) {
+    const int total = 8 * cin * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i % cout, ci = (i / cout) % cin, k = i / (cout * cin);
+        dense[(size_t)ci * 8 * cout + k * cout + co] = w[i];
+    }
+}
+
+int pcgc_convT_k2s2_h2_pack_weights(const float *weight, int32_t cin, int32_t cout, float scale, float *dense_ws, uint32_t *packed,
+                                    void *stream) {
+    const size_t total = pcgc_convT_k2s2_h2_packed_words(cin, cout);
+    PCGC_REQUIRE(total > 0 && weight && packed && dense_ws && scale > 0.f, "pcgc_convT_k2s2_h2_pack_weights: no h2 kernel for %dx%d", cin, cout);
+    gather_up_weights_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(weight, cin, cout, dense_ws);
+    pack_weights_h2_kernel<<<grid_for((int64_t)total / 2, 256, 4), 256, 0, (cudaStream_t)stream>>>(dense_ws, 1, cin, 8 * cout, 0, scale, packed);
+    return check_launch("pack_weights_h2");
+}
+
+int pcgc_convT_k2s2_h2_fwd(const uint32_t *in_h2, int32_t in_ld, int64_t n_in, const uint32_t *packed, float inv_scale,
+                           const float *bias8, int32_t cin, int32_t cout, float *out, int32_t out_ld, uint32_t *out_h2,
+                           int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream) {
+    PCGC_REQUIRE(n_in >= 0 && up_h2_shape(cin, cout) && in_ld >= cin, "pcgc_convT_k2s2_h2_fwd: bad shape n=%lld %dx%d", (long long)n_in, cin,
+                 cout);
+    if (n_in == 0) return PCGC_OK;
+    PCGC_REQUIRE(in_h2 && packed && (out || out_h2), "pcgc_convT_k2s2_h2_fwd: null pointer");
+    PCGC_REQUIRE((in_ld % 4 == 0) && (((uintptr_t)in_h2 & 15) == 0) && (((uintptr_t)packed & 15) == 0),
+                 "pcgc_convT_k2s2_h2_fwd: input rows must be 16-byte aligned");
+    // the 8 child rows of one input row must be one contiguous row of 8 * cout values
+    PCGC_REQUIRE(!out || (out_ld == cout && ((uintptr_t)out & 7) == 0), "pcgc_convT_k2s2_h2_fwd: out must be contiguous [8n, cout]");
+    PCGC_REQUIRE(!out_h2 || (out_h2_ld == cout && cout % 4 == 0 && ((uintptr_t)out_h2 & 15) == 0),
+                 "pcgc_convT_k2s2_h2_fwd: out_h2 must be contiguous [8n, cout]");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nc = 8 * cout;
+    if (cin == 16) return launch_dense_h2<16>(in_h2, in_ld, n_in, packed, nc, inv_scale, bias8, out, nc, out_h2, nc, flags, overflow, s);
+    if (cin == 32) return launch_dense_h2<32>(in_h2, in_ld, n_in, packed, nc, inv_scale, bias8, out, nc, out_h2, nc, flags, overflow, s);
+    return launch_dense_h2<64>(in_h2, in_ld, n_in, packed, nc, inv_scale, bias8, out, nc, out_h2, nc, flags, overflow, s);
 }
 
 int pcgc_conv_k3_octet_h2_supported(int32_t cin, int32_t cout) { return octet_h2_shape(cin, cout) ? 1 : 0; }

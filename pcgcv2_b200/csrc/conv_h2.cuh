@@ -88,8 +88,9 @@ static __global__ void join_h2_kernel(const uint32_t *__restrict__ in, int in_ld
     }
 }
 
-template <int CIN, int COUT, bool NT_, int RG_, int D_, int WARPS_>
+template <int CIN, int COUT, bool NT_, int RG_, int D_, int WARPS_, int KV_ = 27>
 struct H2Cfg {
+    static constexpr int KV = KV_;                                    // kernel volume: 27 (k=3) or 8 (k=2 stride 2: child slots)
     static_assert(CIN % 16 == 0, "h2 kernel: CIN must be a multiple of 16");
     static_assert(NT_ || COUT % 16 == 0, "h2 kernel, T formulation: COUT must be a multiple of 16");
     static constexpr bool NT = NT_;
@@ -102,8 +103,8 @@ struct H2Cfg {
     static constexpr int THREADS = 32 * WARPS;
     static constexpr int ROWS_PER_CTA = WARPS * RPW;
     static constexpr int W_OFF = KS * CT * (NT ? 128 : 256);          // packed 32-bit words per offset (hi + lo)
-    static constexpr size_t packed_words() { return (size_t)27 * W_OFF; }
-    static constexpr size_t smem_bytes() { return packed_words() * 4 + (size_t)WARPS * 27 * RPW * 4; }
+    static constexpr size_t packed_words() { return (size_t)KV * W_OFF; }
+    static constexpr size_t smem_bytes() { return packed_words() * 4 + (size_t)WARPS * KV * RPW * 4; }
 };
 
 // physical input channel of logical pair slot (q, t, half h in 0..1, element e in 0..1): 16q + 4t + 2h + e
@@ -188,20 +189,20 @@ struct H2Epilogue {
     }
 };
 
-template <int CIN, int COUT, bool NT, int RG, int D, int WARPS, int MINB>
+template <int CIN, int COUT, bool NT, int RG, int D, int WARPS, int MINB, int KV = 27>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 conv_k3_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__restrict__ nbr, int64_t n,
                   const uint32_t *__restrict__ packed, float inv_scale, const float *__restrict__ bias,
                   const float *__restrict__ residual, int res_ld, float *__restrict__ out, int out_ld,
                   uint32_t *__restrict__ out_h2, int out_h2_ld, int flags, int *__restrict__ overflow) {
-    using C = H2Cfg<CIN, COUT, NT, RG, D, WARPS>;
+    using C = H2Cfg<CIN, COUT, NT, RG, D, WARPS, KV>;
     constexpr int KS = C::KS, CT = C::CT, NR = C::NR, RPW = C::RPW, W_OFF = C::W_OFF;
     constexpr bool IDXV = NR == 2 || NR == 4;                         // lane's NR kernel-map entries adjacent in smem
     extern __shared__ __align__(16) uint32_t wsm_h2[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    int32_t *idx_s = reinterpret_cast<int32_t *>(wsm_h2 + C::packed_words()) + warp * 27 * RPW;
+    int32_t *idx_s = reinterpret_cast<int32_t *>(wsm_h2 + C::packed_words()) + warp * KV * RPW;
 
-    for (int i = threadIdx.x; i < 27 * W_OFF / 4; i += C::THREADS) cp_async16(wsm_h2 + 4 * i, packed + 4 * i, true);
+    for (int i = threadIdx.x; i < KV * W_OFF / 4; i += C::THREADS) cp_async16(wsm_h2 + 4 * i, packed + 4 * i, true);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
@@ -223,14 +224,14 @@ conv_k3_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__r
                 for (int64_t off = (int64_t)threadIdx.x * 128; off < bytes; off += C::THREADS * 128)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
                 constexpr int LPS = (C::ROWS_PER_CTA * 4 + 127) / 128;
-                for (int i = threadIdx.x; i < 27 * LPS; i += C::THREADS) {
+                for (int i = threadIdx.x; i < KV * LPS; i += C::THREADS) {
                     const int k = i / LPS, l = i % LPS;
                     if ((int64_t)l * 32 < rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(nbr + (int64_t)k * n + r0 + l * 32));
                 }
             }
         }
         __syncwarp();
-        for (int i = lane; i < 27 * RPW; i += 32) {                   // this warp's slice of the kernel map, coalesced
+        for (int i = lane; i < KV * RPW; i += 32) {                   // this warp's slice of the kernel map, coalesced
             const int k = i / RPW, rr = i % RPW;                      // local row rr = 8j + g (j-th gathered row of lane group g)
             const int32_t v = row0 + rr < n ? __ldg(nbr + (int64_t)k * n + row0 + rr) : -1;
             idx_s[IDXV ? k * RPW + (rr & 7) * NR + (rr >> 3) : i] = v >= 0 ? v * ld16 : -1;
@@ -263,7 +264,7 @@ conv_k3_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__r
             int32_t id[NR];
 #pragma unroll
             for (int j = 0; j < NR; ++j) id[j] = idn[j];
-            if (o + 1 < 27) load_idx(o + 1);                          // one offset ahead: its LDS latency hides behind this offset's math
+            if (o + 1 < KV) load_idx(o + 1);                          // one offset ahead: its LDS latency hides behind this offset's math
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
                 const bool ok = id[j] >= 0;
@@ -329,12 +330,12 @@ conv_k3_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__r
 #pragma unroll
         for (int o = 0; o < D - 1; ++o) gather(o, o);
 #pragma unroll 1
-        for (int ob = 0; ob < 27; ob += D) {
+        for (int ob = 0; ob < KV; ob += D) {
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 const int o = ob + d;
-                if (o < 27) {
-                    if (o + D - 1 < 27) gather(o + D - 1, (d + D - 1) % D);
+                if (o < KV) {
+                    if (o + D - 1 < KV) gather(o + D - 1, (d + D - 1) % D);
                     math(o, d);
                 }
             }
@@ -381,6 +382,87 @@ conv_k3_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__r
                     epi.store_pair(row, co, odd ? r0 : v[0], odd ? v[1] : r0);
                     epi.store_pair(row, co + 8, odd ? r1 : v[2], odd ? v[3] : r1);
                 }
+        }
+    }
+    if (epi.over && overflow) *overflow = 1;
+}
+
+// ---- dense product over h2 rows: out[n, NC] = X[n, CIN] * W[CIN, NC]  (no gather) -----------------------------------
+// The generative transposed convolution (ME.MinkowskiGenerativeConvolutionTranspose k=2 s=2, autoencoder.py:155,182,
+// 209) IS this product: input row i makes the 8 child rows 8i..8i+7, i.e. one row of NC = 8 * COUT values with
+// W[ci][k * COUT + co] = kernel[k][ci][co]; the [8n, COUT] child tensor is the same memory as [n, 8 * COUT].
+// T formulation of conv_k3_h2_kernel with the weights resident in shared memory: a warp loads the h2 fragments of
+// its rows once and walks the NC / 16 output tiles, finishing (bias, ReLU, fp32 + h2 stores) each tile at once.
+template <int CIN, int RG_, int WARPS_>
+struct DenseH2Cfg {
+    static_assert(CIN % 16 == 0, "dense h2 kernel: CIN must be a multiple of 16");
+    static constexpr int KS = CIN / 16, RG = RG_, WARPS = WARPS_, THREADS = 32 * WARPS_;
+    static constexpr int ROWS_PER_CTA = WARPS * 8 * RG;
+    static constexpr size_t packed_words(int nc) { return (size_t)KS * (nc / 16) * 256; }
+    static constexpr size_t smem_bytes(int nc) { return packed_words(nc) * 4; }
+};
+
+template <int CIN, int RG, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+dense_h2_kernel(const uint32_t *__restrict__ in, int in_ld, int64_t n, const uint32_t *__restrict__ packed, int nc,
+                float inv_scale, const float *__restrict__ bias, float *__restrict__ out, int out_ld,
+                uint32_t *__restrict__ out_h2, int out_h2_ld, int flags, int *__restrict__ overflow) {
+    using C = DenseH2Cfg<CIN, RG, WARPS>;
+    constexpr int KS = C::KS;
+    extern __shared__ __align__(16) uint32_t wsm_dense[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int CT = nc >> 4;
+    for (int i = threadIdx.x; i < KS * CT * 64; i += C::THREADS) cp_async16(wsm_dense + 4 * i, packed + 4 * i, true);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    H2Epilogue epi{bias, nullptr, out, out_h2, 0, out_ld, out_h2_ld, flags, inv_scale};
+    const bool odd = g & 1;
+    const int64_t n_tiles = (n + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * C::ROWS_PER_CTA + warp * 8 * RG;
+        uint4 x[RG][KS];
+#pragma unroll
+        for (int r = 0; r < RG; ++r) {
+            const int64_t row = row0 + 8 * r + g;
+#pragma unroll
+            for (int q = 0; q < KS; ++q)
+                x[r][q] = row < n ? __ldg(reinterpret_cast<const uint4 *>(in + row * in_ld + 16 * q + 4 * t)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll 2
+        for (int c = 0; c < CT; ++c) {
+            float part[RG][4], small[RG][4];
+#pragma unroll
+            for (int r = 0; r < RG; ++r)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) small[r][e] = 0.f;
+#pragma unroll
+            for (int q = 0; q < KS; ++q) {
+                const uint4 *wp = reinterpret_cast<const uint4 *>(wsm_dense + (q * CT + c) * 256) + lane;
+                const uint4 wh = wp[0], wl = wp[32];
+#pragma unroll
+                for (int r = 0; r < RG; ++r) mma_f16(small[r], wh.x, wh.y, wh.z, wh.w, x[r][q].z, x[r][q].w);
+#pragma unroll
+                for (int r = 0; r < RG; ++r) {
+                    if (q == 0) mma_f16_zero(part[r], wh.x, wh.y, wh.z, wh.w, x[r][q].x, x[r][q].y);
+                    else mma_f16(part[r], wh.x, wh.y, wh.z, wh.w, x[r][q].x, x[r][q].y);
+                }
+#pragma unroll
+                for (int r = 0; r < RG; ++r) mma_f16(small[r], wl.x, wl.y, wl.z, wl.w, x[r][q].x, x[r][q].y);
+            }
+#pragma unroll
+            for (int r = 0; r < RG; ++r) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = part[r][e] + small[r][e];
+                const float r0 = __shfl_xor_sync(0xffffffffu, odd ? v[0] : v[1], 4);
+                const float r1 = __shfl_xor_sync(0xffffffffu, odd ? v[2] : v[3], 4);
+                const int64_t row = row0 + 8 * r + 2 * t + (odd ? 1 : 0);
+                if (row >= n) continue;
+                const int co = 16 * c + (g & ~1);
+                epi.store_pair(row, co, odd ? r0 : v[0], odd ? v[1] : r0);
+                epi.store_pair(row, co + 8, odd ? r1 : v[2], odd ? v[3] : r1);
+            }
         }
     }
     if (epi.over && overflow) *overflow = 1;

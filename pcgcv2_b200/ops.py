@@ -364,6 +364,79 @@ def conv_k3_h2(feats_h2, nbr, pw: PackedK3H2, bias=None, residual=None, relu=Fal
 _SUPPORT = {}
 
 
+def _h2_scale(weight):
+    wmax = float(weight.abs().max())
+    k = int(np.floor(np.log2(16384.0 / wmax))) if wmax > 0 and np.isfinite(wmax) else 0
+    k = max(-24, min(24, k))
+    return float(2.0 ** k), float(2.0 ** -k)
+
+
+class PackedDownH2:
+    """k=2 stride-2 weights [8, cin, cout] split into f16 hi/lo fragments for pcgc_conv_k2s2_h2_fwd (None: no kernel)."""
+
+    def __init__(self, weight: torch.Tensor):
+        assert weight.dim() == 3 and weight.shape[0] == 8 and weight.is_contiguous()
+        self.cin, self.cout = int(weight.shape[1]), int(weight.shape[2])
+        n = int(_lib.lib().pcgc_conv_k2s2_h2_packed_words(self.cin, self.cout))
+        self.packed = None
+        if n:
+            self.scale, self.inv_scale = _h2_scale(weight)
+            self.packed = torch.empty(n, dtype=torch.int32, device=weight.device)
+            check(_lib.lib().pcgc_conv_k2s2_h2_pack_weights(_p(weight), self.cin, self.cout, self.scale, _p(self.packed), _stream()),
+                  "pcgc_conv_k2s2_h2_pack_weights")
+
+
+def child_map_k2(child_keys, parent_of, n_parents):
+    """int32 [8, n_parents]: row of child k = key & 7 of every parent, -1 where the child is absent."""
+    n = child_keys.shape[0]
+    cm = torch.full((8, n_parents), -1, dtype=torch.int32, device=child_keys.device)
+    cm[(child_keys & 7), parent_of.long()] = torch.arange(n, dtype=torch.int32, device=child_keys.device)
+    return cm
+
+
+def conv_k2s2_h2(feats_h2, child_map, pw: PackedDownH2, bias=None, relu=False, want_f32=True, want_h2=True, overflow=None):
+    """k=2 stride-2 convolution over h2 features on the tensor cores -> (fp32 out or None, h2 out or None)."""
+    x = _h2(feats_h2)
+    n_par = child_map.shape[1]
+    assert x.shape[1] == pw.cin and pw.packed is not None and child_map.shape[0] == 8 and child_map.is_contiguous()
+    out = torch.empty((n_par, pw.cout), dtype=torch.float32, device=x.device) if want_f32 else None
+    out_h2 = torch.empty((n_par, pw.cout), dtype=torch.int32, device=x.device) if want_h2 else None
+    check(_lib.lib().pcgc_conv_k2s2_h2_fwd(_p(x), x.stride(0), _p(child_map), n_par, _p(pw.packed), pw.inv_scale, _p(bias), pw.cin,
+                                           pw.cout, _p(out), pw.cout, _p(out_h2), pw.cout, EPI_RELU if relu else 0, _p(overflow),
+                                           _stream()), "pcgc_conv_k2s2_h2_fwd")
+    return out, out_h2
+
+
+class PackedUpH2:
+    """transposed k=2 stride-2 weights [8, cin, cout] as the dense [cin, 8*cout] operand, split and packed (None: no kernel)."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None):
+        assert weight.dim() == 3 and weight.shape[0] == 8 and weight.is_contiguous()
+        self.cin, self.cout = int(weight.shape[1]), int(weight.shape[2])
+        n = int(_lib.lib().pcgc_convT_k2s2_h2_packed_words(self.cin, self.cout))
+        self.packed = None
+        if n:
+            self.scale, self.inv_scale = _h2_scale(weight)
+            self.packed = torch.empty(n, dtype=torch.int32, device=weight.device)
+            ws = torch.empty(8 * self.cin * self.cout, dtype=torch.float32, device=weight.device)
+            check(_lib.lib().pcgc_convT_k2s2_h2_pack_weights(_p(weight), self.cin, self.cout, self.scale, _p(ws), _p(self.packed),
+                                                             _stream()), "pcgc_convT_k2s2_h2_pack_weights")
+            self.bias8 = None if bias is None else bias.reshape(1, -1).repeat(1, 8).contiguous()
+
+
+def convT_k2s2_h2(feats_h2, pw: PackedUpH2, relu=False, want_f32=True, want_h2=True, overflow=None):
+    """generative transposed k=2 stride-2 convolution as one dense tensor-core product -> ([8n, cout] fp32, h2)."""
+    x = _h2(feats_h2)
+    n = x.shape[0]
+    assert x.shape[1] == pw.cin and pw.packed is not None
+    out = torch.empty((8 * n, pw.cout), dtype=torch.float32, device=x.device) if want_f32 else None
+    out_h2 = torch.empty((8 * n, pw.cout), dtype=torch.int32, device=x.device) if want_h2 else None
+    check(_lib.lib().pcgc_convT_k2s2_h2_fwd(_p(x), x.stride(0), n, _p(pw.packed), pw.inv_scale, _p(pw.bias8), pw.cin, pw.cout, _p(out),
+                                            pw.cout, _p(out_h2), pw.cout, EPI_RELU if relu else 0, _p(overflow), _stream()),
+          "pcgc_convT_k2s2_h2_fwd")
+    return out, out_h2
+
+
 def octet_h2_supported(cin, cout) -> bool:
     key = ("octet_h2", int(cin), int(cout))
     if key not in _SUPPORT:

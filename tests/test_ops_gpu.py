@@ -459,6 +459,50 @@ def test_rowlane_layers_write_h2_copy_in_epilogue():
     assert int(flag.item()) == 1
 
 
+def test_k2s2_and_transposed_layers_on_tensor_cores_vs_oracle():
+    """k=2 stride-2 convolution as the h2 gather kernel over the 8 child slots, and its generative transpose as ONE
+    dense h2 product, against the oracle (ragged child counts, tile tails, both outputs)."""
+    g = torch.Generator().manual_seed(21)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    c = _surface()[:6001]
+    keys, order = ops.argsort_u64(_keys(c))
+    cs = c[order.cpu().numpy()]
+    for cin, cout in ((16, 32), (32, 64), (64, 32)):
+        pk, rows, off, parent_of = ops.stride_down(keys, keys_are_sorted=True, with_parent_of=True)
+        f = torch.randn(len(c), cin, generator=g) * 2.0
+        w = torch.randn(8, cin, cout, generator=g) / np.sqrt(8 * cin)
+        b = torch.randn(1, cout, generator=g)
+        ref, ref_c = S.conv_k2s2(f, cs, 1, w, b)
+        pw = ops.PackedDownH2(w.to(DEV))
+        assert pw.packed is not None
+        cmap = ops.child_map_k2(keys, parent_of, len(pk))
+        assert int((cmap >= 0).sum()) == len(c)
+        got, got_h = ops.conv_k2s2_h2(ops.split_h2(f.to(DEV)), cmap, pw, b.to(DEV), relu=True, overflow=flag)
+        got_c = ops.unpack_keys(pk, 2).cpu().numpy()
+        want, _ = _sorted_by_coords(torch.relu(ref), ref_c)
+        have, _ = _sorted_by_coords(got.cpu(), got_c)
+        assert _rel_err(have, want) < H2_TOL
+        assert _rel_err(ops.join_h2(got_h), got.cpu()) < 1e-6
+    for cin, cout, n in ((64, 32, 1001), (32, 16, 4099), (16, 8, 7), (32, 64, 300)):
+        f = torch.randn(n, cin, generator=g) * 2.0
+        w = torch.randn(8, cin, cout, generator=g) / np.sqrt(cin)
+        b = torch.randn(1, cout, generator=g)
+        want = ops.convT_k2s2(f.to(DEV), w.to(DEV), b.to(DEV), relu=True)          # fp32 kernel (oracle-checked elsewhere)
+        pu = ops.PackedUpH2(w.to(DEV), b.to(DEV))
+        assert pu.packed is not None
+        got, got_h = ops.convT_k2s2_h2(ops.split_h2(f.to(DEV)), pu, relu=True, overflow=flag)
+        assert got.shape == (8 * n, cout) and _rel_err(got, want.cpu()) < H2_TOL
+        assert _rel_err(ops.join_h2(got_h), got.cpu()) < 1e-6
+        only_h = ops.convT_k2s2_h2(ops.split_h2(f.to(DEV)), pu, relu=True, want_f32=False)
+        assert only_h[0] is None and torch.equal(only_h[1], got_h)
+    assert int(flag.item()) == 0
+
+
+def _sorted_by_coords(feats, coords):
+    order = np.lexsort(np.asarray(coords).T[::-1])
+    return feats[torch.from_numpy(order)], np.asarray(coords)[order]
+
+
 def test_conv_k3_h2_overflow_flag_and_small_weights():
     """tiny weights keep their precision through the power-of-two scale; an output beyond the f16 range raises the flag."""
     c = _surface()[:4001]
