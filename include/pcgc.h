@@ -240,6 +240,37 @@ int pcgc_convT_k2s2_fwd_h2out(const float *in, int32_t in_ld, int64_t n_in, cons
                               int32_t cin, int32_t cout, float *out, int32_t out_ld, uint32_t *out_h2,
                               int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream);
 
+/* ---- one InceptionResNet block (autoencoder.py:52-57) per call: out = cat(conv0_1(relu(conv0_0(x))),
+ * conv1_2(relu(conv1_1(relu(conv1_0(x)))))) + x.  The caller resolves once per layer which kernel serves it (route)
+ * and passes that kernel's packed weights; the call issues exactly the launches the per-layer entry points would
+ * (same kernels, same order, same results) without a host round trip per layer.  Layers 0..2 = conv0_0, conv0_1,
+ * conv1_1 (k=3); w1/b1 = conv1_0, conv1_2 (k=1, reference layout).  x_h2 / out_h2 may be NULL when no layer needs /
+ * the caller does not want the h2 copy.  ws: pcgc_irn_ws_bytes(n, c) bytes of device memory for the temporaries. */
+enum { PCGC_ROUTE_H2_GATHER = 0, PCGC_ROUTE_H2_OCTET = 1, PCGC_ROUTE_TF32_GATHER = 2, PCGC_ROUTE_TF32_OCTET = 3, PCGC_ROUTE_FP32 = 4 };
+typedef struct pcgc_irn_args {
+    int64_t n;                      /* rows of the coordinate set */
+    int32_t c;                      /* block channels (16, 32, 64) */
+    int32_t reserved;
+    const int32_t *nbr;             /* [27][n] kernel map of the set (gather routes), or NULL */
+    const int32_t *parent_nbr;      /* [27][n/8] kernel map of the parent set (octet routes), or NULL */
+    const float *x;                 /* block input fp32, leading dimension x_ld */
+    const uint32_t *x_h2;           /* block input h2, leading dimension x_h2_ld */
+    float *out;                     /* block output fp32 [n][c] */
+    uint32_t *out_h2;               /* block output h2, or NULL */
+    int32_t x_ld, x_h2_ld, out_ld, out_h2_ld;
+    int32_t route[3];               /* PCGC_ROUTE_* of conv0_0, conv0_1, conv1_1 */
+    float inv_scale[3];             /* of the h2 routes */
+    const void *w3[3];              /* packed weights for the route (fp32 `kernel` for PCGC_ROUTE_FP32) */
+    const float *b3[3];
+    const float *w1[2];
+    const float *b1[2];
+    void *ws;
+    size_t ws_bytes;
+    int32_t *overflow;              /* device flag of the h2 kernels, or NULL */
+} pcgc_irn_args;
+size_t pcgc_irn_ws_bytes(int64_t n, int32_t c);
+int pcgc_irn_fwd(const pcgc_irn_args *args, void *stream);
+
 /* ---- backward passes (row a16; MinkowskiEngine Convolution*Backward driven by trainer.py:136) -----
  * Input gradients of the k=3 and k=1 convolutions are forward convolutions of grad_out with the
  * transposed weights (offset-flipped for k=3: W'[k] = W[26-k]^T; stride-1 kernel maps are symmetric),

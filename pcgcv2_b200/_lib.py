@@ -82,6 +82,8 @@ SIGNATURES = {
     "pcgc_conv_k2s2_fwd_h2out": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32,
                                                  c_p, c_p]),
     "pcgc_convT_k2s2_fwd_h2out": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_p]),
+    "pcgc_irn_ws_bytes": (c_sz, [c_i64, c_i32]),
+    "pcgc_irn_fwd": (ctypes.c_int, [c_p, c_p]),
     "pcgc_conv_bwd_weight": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_i32, c_p, c_p]),
     "pcgc_conv_k2s2_bwd": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_i64, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_p]),
     "pcgc_convT_k2s2_bwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_p]),
@@ -100,6 +102,16 @@ SIGNATURES = {
     "pcgc_rc_encode_u16_host": (c_i64, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
     "pcgc_rc_decode_u16_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
 }
+
+class IrnArgs(ctypes.Structure):
+    """pcgc_irn_args (include/pcgc.h)."""
+    _fields_ = [("n", c_i64), ("c", c_i32), ("reserved", c_i32), ("nbr", c_p), ("parent_nbr", c_p), ("x", c_p), ("x_h2", c_p),
+                ("out", c_p), ("out_h2", c_p), ("x_ld", c_i32), ("x_h2_ld", c_i32), ("out_ld", c_i32), ("out_h2_ld", c_i32),
+                ("route", c_i32 * 3), ("inv_scale", ctypes.c_float * 3), ("w3", c_p * 3), ("b3", c_p * 3), ("w1", c_p * 2),
+                ("b1", c_p * 2), ("ws", c_p), ("ws_bytes", c_sz), ("overflow", c_p)]
+
+
+ROUTE_H2_GATHER, ROUTE_H2_OCTET, ROUTE_TF32_GATHER, ROUTE_TF32_OCTET, ROUTE_FP32 = range(5)
 
 _lib = None
 

@@ -15,12 +15,13 @@ leaves the device between layers.
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass, field
 
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 @dataclass
@@ -84,7 +85,7 @@ _FULL = _FullOctets()            # "a full-octet level" for kernel-routing quest
 
 
 class Codec:
-    def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True, use_h2=True):
+    def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True, use_h2=True, fuse_irn=True):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("pcgcv2_b200.Codec runs on a CUDA device only (there is no CPU path)")
@@ -139,6 +140,8 @@ class Codec:
         self.use_octet = use_octet_kernels
         self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)   # raised by an h2 producer: re-run in fp32
         self.h2_fallbacks = 0
+        self.fuse_irn = fuse_irn        # InceptionResNet blocks through pcgc_irn_fwd (one C call per block)
+        self._irn_plans = {}
         self._pinned = {}               # reusable pinned host staging buffers (decoded coordinates, symbols, flags)
         self._tables = {}               # (lo, hi) -> host CDF table
         self._dedupe_next = False
@@ -234,9 +237,72 @@ class Codec:
             return False
         return ph.gather
 
+    # ---- one InceptionResNet block per C call (csrc/irn.cpp): same kernels, same order, no Python between the launches
+    def _route(self, name, full_octets, aligned=True):
+        """(route code, packed weights tensor, inverse weight scale) of one k=3 layer -- the decision ``_k3`` takes."""
+        ph = self.packed_h2.get(name) if self._h2_on else None
+        if ph is not None and full_octets and self.use_octet and ops.octet_h2_supported(ph.cin, ph.cout):
+            return _lib.ROUTE_H2_OCTET, ph.packed, ph.inv_scale
+        if ph is not None and not ph.gather:
+            ph = None
+        po = self.packed_octet.get(name) if (full_octets and aligned) else None
+        if po is not None:
+            return _lib.ROUTE_TF32_OCTET, po.packed, 1.0
+        if ph is not None:
+            return _lib.ROUTE_H2_GATHER, ph.packed, ph.inv_scale
+        pw = self.packed.get(name) if aligned else None
+        if pw is not None:
+            return _lib.ROUTE_TF32_GATHER, pw.packed, 1.0
+        return _lib.ROUTE_FP32, self.w[name + ".kernel"], 1.0
+
+    def _irn_plan(self, prefix, full_octets):
+        key = (prefix, full_octets, self._h2_on)
+        plan = self._irn_plans.get(key)
+        if plan is None:
+            args = _lib.IrnArgs()
+            keep = []                                                 # tensors the struct points into
+            for i, leaf in enumerate((".conv0_0", ".conv0_1", ".conv1_1")):
+                route, w, inv = self._route(prefix + leaf, full_octets)
+                args.route[i], args.inv_scale[i] = route, inv
+                args.w3[i], args.b3[i] = w.data_ptr(), self.w[prefix + leaf + ".bias"].data_ptr()
+                keep.append(w)
+            for i, leaf in enumerate((".conv1_0", ".conv1_2")):
+                args.w1[i], args.b1[i] = self.w[prefix + leaf + ".kernel"].data_ptr(), self.w[prefix + leaf + ".bias"].data_ptr()
+            routes = list(args.route)
+            plan = self._irn_plans[key] = {
+                "args": args, "keep": keep,
+                "child_map": any(r in (_lib.ROUTE_H2_GATHER, _lib.ROUTE_TF32_GATHER, _lib.ROUTE_FP32) for r in routes),
+                "parent_map": any(r in (_lib.ROUTE_H2_OCTET, _lib.ROUTE_TF32_OCTET) for r in routes),
+                "x_h2": routes[0] in (_lib.ROUTE_H2_GATHER, _lib.ROUTE_H2_OCTET)}
+        return plan
+
+    def _irn_fused(self, prefix, x: _F, level) -> _F:
+        n, c = x.f.shape
+        plan = self._irn_plan(prefix, level.full_octets)
+        a = plan["args"]
+        out = _F(torch.empty((n, c), dtype=torch.float32, device=self.device),
+                 torch.empty((n, c), dtype=torch.int32, device=self.device) if self._h2_on else None)
+        ws = torch.empty(int(_lib.lib().pcgc_irn_ws_bytes(n, c)), dtype=torch.uint8, device=self.device)
+        xh = self._h(x) if plan["x_h2"] else x.h
+        a.n, a.c = n, c
+        a.nbr = level.nbr.data_ptr() if plan["child_map"] else None
+        a.parent_nbr = level.parent.nbr.data_ptr() if plan["parent_map"] else None
+        a.x, a.x_ld = x.f.data_ptr(), x.f.stride(0)
+        a.x_h2, a.x_h2_ld = (xh.data_ptr(), xh.stride(0)) if xh is not None else (None, 0)
+        a.out, a.out_ld = out.f.data_ptr(), c
+        a.out_h2, a.out_h2_ld = (out.h.data_ptr(), c) if out.h is not None else (None, 0)
+        a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
+        a.overflow = self._overflow.data_ptr()
+        _lib.check(_lib.lib().pcgc_irn_fwd(ctypes.byref(a), ops._stream()), "pcgc_irn_fwd")
+        self._rec(prefix, out, level)
+        return out
+
     def _irn(self, prefix, x: _F, level) -> _F:
         """InceptionResNet (autoencoder.py:52-57) as 5 fused launches: the two branch outputs are
         written straight into the halves of the result with the residual added in the epilogue."""
+        if (self.fuse_irn and self.record is None and x.f is not None and x.f.stride(0) % 4 == 0
+                and not any(k.startswith(prefix) for k in self.probe)):      # per-layer recording / probing: layer by layer
+            return self._irn_fused(prefix, x, level)
         c = x.f.shape[1]
         h = c // 2
         out = _F(torch.empty_like(x.f))

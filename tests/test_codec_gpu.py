@@ -216,3 +216,17 @@ def test_frame_pipeline_matches_single_frame_path(r3):
         with pytest.raises(Exception):
             pipe.roundtrip([np.zeros((4, 2), dtype=np.int32)])    # a worker's error reaches the caller
         assert len(pipe.roundtrip(frames[:1])) == 1               # and the pipeline stays usable
+
+
+@pytest.mark.parametrize("use_h2", [True, False])
+def test_irn_block_per_c_call_is_the_same_computation(r3, use_h2):
+    """pcgc_irn_fwd (one C call per InceptionResNet block) issues the kernels the layer-by-layer path issues:
+    bit-identical bitstream, bottleneck and decoded set; with and without the h2 kernels; also without octet kernels."""
+    pts = synth.ellipsoid_vox8()
+    for octet in (True, False):
+        fused = Codec(r3, use_h2=use_h2, use_octet_kernels=octet, fuse_irn=True)
+        plain = Codec(r3, use_h2=use_h2, use_octet_kernels=octet, fuse_irn=False)
+        a, b = fused.encode(pts), plain.encode(pts)
+        assert a.F == b.F and a.H == b.H and (a.coords == b.coords).all() and fused._irn_plans and not plain._irn_plans
+        da, db = fused.decode(a, to_host=False), plain.decode(b, to_host=False)
+        assert torch.equal(da, db)                                # same rows in the same order
