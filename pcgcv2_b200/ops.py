@@ -675,12 +675,17 @@ def eb_cdf_table(params: torch.Tensor, min_v: int, max_v: int):
     return cdf, u16
 
 
+_MM_INIT = {}
+
+
 def eb_quantize_async(feats: torch.Tensor):
     """round -> (symbols int16 [N,C], minmax int32 [2]) on the device, no synchronisation."""
     feats = _feat(feats).contiguous()
     count = feats.numel()
-    mm = torch.empty(2, dtype=torch.int32, device=feats.device)
-    mm[0], mm[1] = 2 ** 31 - 1, -2 ** 31
+    init = _MM_INIT.get(feats.device)
+    if init is None:                       # (a scalar assignment would be a pageable H2D copy: a stream synchronisation)
+        init = _MM_INIT[feats.device] = torch.tensor([2 ** 31 - 1, -2 ** 31], dtype=torch.int32, device=feats.device)
+    mm = init.clone()
     L = _lib.lib()
     check(L.pcgc_eb_round_minmax(_p(feats), count, _p(mm), _stream()), "pcgc_eb_round_minmax")
     sym = torch.empty(feats.shape, dtype=torch.int16, device=feats.device)
