@@ -47,10 +47,14 @@ struct OctetH2Tune {
     // measured on B200 (tools/profile_octet_h2.py, 1.69 M-row decoder level, profiles/r01_h2_sweep.txt):
     // 16x4 0.217 ms at RG 2 / 8 warps vs 0.250 at RG 1 / 16 warps (the loop is shared-memory bound: a bigger row group
     // re-uses each weight LDS); 16x16 0.297 vs 0.307; 16x32 0.477 vs 0.424 (registers)
-    static constexpr bool kBig = NT || COUT == 16;                // default: the bigger row group
-    static constexpr bool kUseBig = V != 2 && ((V == 0) == kBig);
-    static constexpr int RG = NT ? (kUseBig ? 2 : 1) : (kUseBig ? 4 : 2);
-    static constexpr int WARPS = V == 2 ? 20 : (kUseBig ? 8 : 16);
+    // V0 (default): one halo buffer per warp, the biggest row group that fits (the loop is shared-memory bound: a bigger
+    // group re-uses each weight LDS).  V1 / V2: double-buffered halos (the next tile is staged during the MMAs) with the
+    // smaller row groups that leaves room for -- measured SLOWER on B200 (profiles/r01_h2_sweep.txt: 16x16 0.301 ms vs
+    // 0.370 / 0.400; 16x4 0.217 vs 0.311 / 0.238), i.e. the halo latency is already hidden by the other warps and the
+    // extra weight reads cost more; kept selectable for the next round's CTA-shared halo work.
+    static constexpr bool DB = V != 0;
+    static constexpr int RG = DB ? (NT ? 1 : 2) : (NT ? 2 : (COUT == 16 ? 4 : 2));
+    static constexpr int WARPS = DB ? (V == 1 ? 10 : 8) : (NT ? 8 : (COUT == 16 ? 8 : 16));
 };
 
 static int octet_h2_variant() {
@@ -68,9 +72,9 @@ static int launch_octet_h2_v(const uint32_t *in, int in_ld, const int32_t *pnbr,
                              float inv_scale, const float *bias, const float *res, int res_ld, float *out, int out_ld,
                              uint32_t *out_h2, int out_h2_ld, int flags, int *overflow, cudaStream_t s) {
     using T = OctetH2Tune<CIN, COUT, V>;
-    using C = OctetH2Cfg<CIN, COUT, T::NT, T::RG, T::WARPS>;
+    using C = OctetH2Cfg<CIN, COUT, T::NT, T::RG, T::WARPS, T::DB>;
     static_assert(C::smem_bytes() <= 227 * 1024, "octet h2 kernel: shared memory budget");
-    auto kern = conv_k3_octet_h2_kernel<CIN, COUT, T::NT, T::RG, T::WARPS, 1>;
+    auto kern = conv_k3_octet_h2_kernel<CIN, COUT, T::NT, T::RG, T::WARPS, 1, T::DB>;
     static int ctas = 0;
     if (ctas == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());

@@ -13,8 +13,9 @@
 
 namespace pcgc {
 
-template <int CIN, int COUT, bool NT_, int RG_, int WARPS_>
+template <int CIN, int COUT, bool NT_, int RG_, int WARPS_, bool DB_ = false>
 struct OctetH2Cfg {
+    static constexpr bool DB = DB_;                               // two halo buffers per warp: the next tile is staged during the MMAs
     static_assert(CIN == 16 || CIN == 32, "octet h2 kernel: CIN in {16, 32}");
     static_assert(NT_ || COUT % 16 == 0, "octet h2 kernel, T formulation: COUT must be a multiple of 16");
     static constexpr bool NT = NT_;
@@ -30,25 +31,35 @@ struct OctetH2Cfg {
     static constexpr int HB = HROWS * ROWB;
     static constexpr int W_OFF = KS * CT * (NT ? 128 : 256);
     static constexpr size_t packed_words() { return (size_t)27 * W_OFF; }
-    static constexpr size_t warp_bytes() { return ((size_t)OW * HB + (size_t)27 * OW * 4 + 127) / 128 * 128; }
+    static constexpr size_t buf_bytes() { return ((size_t)OW * HB + (size_t)27 * OW * 4 + 127) / 128 * 128; }
+    static constexpr size_t warp_bytes() { return (DB ? 2 : 1) * buf_bytes(); }
     static constexpr size_t smem_bytes() { return packed_words() * 4 + (size_t)WARPS * warp_bytes(); }
     static constexpr int OCTETS_PER_CTA = WARPS * OW;
 };
 
-template <int CIN, int COUT, bool NT, int RG, int WARPS, int MINB>
+// wait until the z-planes that kernel-offset plane iz reads have landed, with EXTRA younger cp.async groups (the next
+// tile's four planes) allowed to stay in flight
+template <int EXTRA>
+__device__ __forceinline__ void halo_wait_db(int iz) {
+    if (iz == 0) cp_async_wait<2 + EXTRA>();
+    else if (iz == 1) cp_async_wait<1 + EXTRA>();
+    else cp_async_wait<EXTRA>();
+    __syncwarp();
+}
+
+template <int CIN, int COUT, bool NT, int RG, int WARPS, int MINB, bool DB = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__restrict__ pnbr, int64_t n_par,
                         const uint32_t *__restrict__ packed, float inv_scale, const float *__restrict__ bias,
                         const float *__restrict__ residual, int res_ld, float *__restrict__ out, int out_ld,
                         uint32_t *__restrict__ out_h2, int out_h2_ld, int flags, int *__restrict__ overflow) {
-    using C = OctetH2Cfg<CIN, COUT, NT, RG, WARPS>;
+    using C = OctetH2Cfg<CIN, COUT, NT, RG, WARPS, DB>;
     constexpr int KS = C::KS, CT = C::CT, OW = C::OW, NR = C::NR, ROWB = C::ROWB, PPR = C::PPR;
     constexpr int SY = C::SY, SZ = C::SZ, HB = C::HB, W_OFF = C::W_OFF;
     extern __shared__ __align__(128) unsigned char smem_oh2[];
     uint32_t *wsm = reinterpret_cast<uint32_t *>(smem_oh2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    unsigned char *halo = smem_oh2 + C::packed_words() * 4 + (size_t)warp * C::warp_bytes();
-    int32_t *sidx = reinterpret_cast<int32_t *>(halo + (size_t)OW * HB);            // [27][OW] parent rows of the neighbours
+    unsigned char *halo0 = smem_oh2 + C::packed_words() * 4 + (size_t)warp * C::warp_bytes();   // per buffer: halos, then [27][OW] parent rows
 
     for (int i = threadIdx.x; i < 27 * W_OFF / 4; i += C::THREADS) cp_async16(wsm + 4 * i, packed + 4 * i, true);
     cp_async_commit();
@@ -57,23 +68,41 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
 
     // lane's read base: child g of an octet, 16-byte piece t of each 64-byte chunk (chunk index XOR x parity for wide rows)
     const int cx = g & 1, cy = (g >> 1) & 1, cz = g >> 2;
-    const unsigned char *slot[KS];
+    int slot[KS];                                                   // byte offsets inside a halo buffer
 #pragma unroll
-    for (int s = 0; s < KS; ++s) slot[s] = halo + (cx + SY * cy + SZ * cz) * ROWB + (KS >= 2 ? ((s ^ cx) * 64) : 0) + t * 16;
+    for (int s = 0; s < KS; ++s) slot[s] = (cx + SY * cy + SZ * cz) * ROWB + (KS >= 2 ? ((s ^ cx) * 64) : 0) + t * 16;
 
     const int64_t n_tiles = (n_par + C::OCTETS_PER_CTA - 1) / C::OCTETS_PER_CTA;
     const char *in_bytes = reinterpret_cast<const char *>(in);
     const uint32_t ldb = (uint32_t)in_ld * 4u;
     H2Epilogue epi{bias, residual, out, out_h2, res_ld, out_ld, out_h2_ld, flags, inv_scale};
-    int32_t prow[OW];                                               // parent rows for the NEXT tile (lane k: neighbour k)
+    int32_t prow[OW];                                               // parent rows of the next tile to stage (lane k: neighbour k)
+    auto stage = [&](unsigned char *buf) {                          // rows -> this buffer's index slice -> cp.async of the halos
+        int32_t *sidx = reinterpret_cast<int32_t *>(buf + (size_t)OW * HB);
+        store_parent_rows<OW>(sidx, prow, lane);
+        __syncwarp();
+        halo_fill<PPR, OW, HB, ROWB, SY, SZ, (KS >= 2)>(buf, sidx, in_bytes, ldb, lane);
+    };
     load_parent_rows<OW>(prow, pnbr, n_par, (int64_t)blockIdx.x * C::OCTETS_PER_CTA + warp * OW, lane);
+    int cur = 0;
+    if constexpr (DB) {                                             // prologue: the first tile's halos
+        stage(halo0);
+        load_parent_rows<OW>(prow, pnbr, n_par, ((int64_t)blockIdx.x + gridDim.x) * C::OCTETS_PER_CTA + warp * OW, lane);
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t oct0 = tile * C::OCTETS_PER_CTA + warp * OW;                // first octet of this warp
         __syncwarp();                                                             // previous iteration's readers are done
-        store_parent_rows<OW>(sidx, prow, lane);
-        __syncwarp();
-        halo_fill<PPR, OW, HB, ROWB, SY, SZ, (KS >= 2)>(halo, sidx, in_bytes, ldb, lane);
-        load_parent_rows<OW>(prow, pnbr, n_par, (tile + gridDim.x) * C::OCTETS_PER_CTA + warp * OW, lane);
+        unsigned char *halo;
+        if constexpr (DB) {                // stage tile + gridDim.x into the other buffer: its loads fly during this tile's MMAs
+            halo = halo0 + (size_t)cur * C::buf_bytes();
+            stage(halo0 + (size_t)(cur ^ 1) * C::buf_bytes());                    // (past the end: rows are -1, zero fill, no traffic)
+            load_parent_rows<OW>(prow, pnbr, n_par, (tile + 2 * (int64_t)gridDim.x) * C::OCTETS_PER_CTA + warp * OW, lane);
+            cur ^= 1;
+        } else {
+            halo = halo0;
+            stage(halo0);
+            load_parent_rows<OW>(prow, pnbr, n_par, (tile + gridDim.x) * C::OCTETS_PER_CTA + warp * OW, lane);
+        }
 
         float acc[CT][RG][4], small[CT][RG][4];
 #pragma unroll
@@ -82,7 +111,7 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
             for (int r = 0; r < RG; ++r)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[c][r][e] = small[c][r][e] = 0.f;
-        halo_wait(0);
+        halo_wait_db<DB ? 4 : 0>(0);
 
         uint4 xb[2][NR][KS];
         auto load_frags = [&](int o, uint4 (&x)[NR][KS]) {
@@ -92,12 +121,12 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
             for (int j = 0; j < NR; ++j)
 #pragma unroll
                 for (int q = 0; q < KS; ++q)
-                    x[j][q] = *reinterpret_cast<const uint4 *>(slot[KS >= 2 ? (q ^ (ix & 1)) : 0] + j * HB + doff);
+                    x[j][q] = *reinterpret_cast<const uint4 *>(halo + slot[KS >= 2 ? (q ^ (ix & 1)) : 0] + j * HB + doff);
         };
         load_frags(0, xb[0]);
 #pragma unroll
         for (int o = 0; o < 27; ++o) {
-            if ((o + 1) % 9 == 0 && o + 1 < 27) halo_wait((o + 1) / 9);           // next z-plane of the halo
+            if ((o + 1) % 9 == 0 && o + 1 < 27) halo_wait_db<DB ? 4 : 0>((o + 1) / 9);   // next z-plane of the halo
             if (o + 1 < 27) load_frags(o + 1, xb[(o + 1) & 1]);
             uint4 (&x)[NR][KS] = xb[o & 1];
             const uint32_t *wb = wsm + (size_t)o * W_OFF;
