@@ -18,7 +18,7 @@
 //    is accumulated from zero and joined to the running sum by a round-to-nearest FADD (the tensor core
 //    adds with truncation), exactly like the 3xTF32 kernels.
 //
-// Accuracy (CPU emulation over the whole r3 network on the vox8 known-answer cloud): max|delta|/max|ref|
+// Accuracy (CPU emulation over the whole network, tools/h2_emulation.py, vox8 known-answer cloud): max|delta|/max|ref|
 // <= 1.7e-6 on every layer, bit-identical bitstream and decoded occupancy.  Range: |x| must stay below
 // 65504 (activations of the trained networks peak at ~30); the epilogue raises *overflow when a value
 // leaves the range so that the caller can re-run on the 3xTF32 path instead of returning a wrong result.
