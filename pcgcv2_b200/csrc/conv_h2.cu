@@ -156,11 +156,12 @@ static int launch_dense_h2(const uint32_t *in, int in_ld, int64_t n, const uint3
     using C = DenseH2Cfg<CIN, RG, WARPS>;
     auto kern = dense_h2_kernel<CIN, RG, WARPS, MINB>;
     const size_t smem = C::smem_bytes(nc);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("dense h2 %dx%d: %s", CIN, nc, cudaGetErrorString(e)); return PCGC_ERR_CUDA; }
-        smem_set = smem;
+    // opt in once to the largest weight block any supported shape needs (nc <= 512); a function-local static is
+    // initialised exactly once even when two frame workers arrive here together
+    static const cudaError_t opt_in = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes(512));
+    if (opt_in != cudaSuccess || smem > C::smem_bytes(512)) {
+        set_error("dense h2 %dx%d: %s", CIN, nc, opt_in != cudaSuccess ? cudaGetErrorString(opt_in) : "nc > 512");
+        return PCGC_ERR_CUDA;
     }
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
