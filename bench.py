@@ -207,6 +207,8 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": f"frames sharded over {world} GPU(s), {depth} frame(s) in flight per GPU (one host thread + "
                                   "CUDA stream each: the host range coder of one frame overlaps the kernels of the other)",
                    "serial_ms_per_frame": round(ms_serial / args.steps, 3), "host_cpus": len(os.sched_getaffinity(0)),
+                   "arithmetic": "k=3 / k=2 layers: operands split into f16 hi + f16 lo (22 significand bits), three tensor-core "
+                                 "products per term pair, f32 accumulation; remaining layers fp32 / 3xTF32",
                    "bpp_features": round(total_bits / total_pts, 5),
                    "coords_side_channel": "raw int32 hand-over (tmc3 subprocess out of scope)",
                    "l2": "per-step traffic (~8.6 GB algorithmic, >1 GB live) exceeds the 126 MB L2; no flush needed"},
