@@ -58,6 +58,12 @@ uint64_t pcgc_launch_count(void);
  * non-multiple of the stride. */
 int pcgc_pack_keys(const int32_t *coords, int64_t n, int32_t tensor_stride, uint64_t *keys,
                    int32_t *err_flag, void *stream);
+
+/* scale_sparse_tensor(x, factor) -- data_utils.py:112-118 (coder.py:149-152,166-167): every
+ * coordinate value v -> (int) round_half_even((float) v * factor); `count` = number of int32
+ * values (rows x columns; pass the spatial columns only).  The duplicate rows the down-scaling
+ * creates collapse at the following coordinate-map insertion (pcgc_hash_build / Codec.encode). */
+int pcgc_scale_coords(const int32_t *coords, int64_t count, float factor, int32_t *out, void *stream);
 int pcgc_unpack_keys(const uint64_t *keys, int64_t n, int32_t tensor_stride, int32_t *coords,
                      void *stream);
 
@@ -347,6 +353,26 @@ int64_t pcgc_rc_encode_u16_host(const uint16_t *cdf_u16_host, int64_t n_tables, 
                                 const int16_t *sym_host, int64_t n_sym, uint8_t *out_host, int64_t cap);
 int pcgc_rc_decode_u16_host(const uint16_t *cdf_u16_host, int64_t n_tables, int32_t lp,
                             const uint8_t *in_host, int64_t in_len, int16_t *sym_host, int64_t n_sym);
+
+/* ---- ASCII PLY geometry I/O (row f2; HOST functions, synchronous) ---------------------------
+ * read_ply_ascii_geo / write_ply_ascii_geo -- data_utils.py:19-48 (coder.py:26,33,128,177).
+ * The reader keeps the reference's line semantics: a line is split at single spaces; if any
+ * token fails to parse as a float the whole line is skipped (header, comments); the first
+ * three values are truncated toward zero.  count_lines gives the row capacity to allocate;
+ * parse returns the number of vertex rows written to coords_host (int32 [rows][3]);
+ * format writes header + "x y z\n" lines and returns the byte count (cap >= 160 + 36 n). */
+int64_t pcgc_ply_count_lines_host(const char *text_host, int64_t len);
+int64_t pcgc_ply_parse_ascii_host(const char *text_host, int64_t len, int32_t *coords_host, int64_t cap_rows);
+int64_t pcgc_ply_format_ascii_host(const int32_t *coords_host, int64_t n, char *text_host, int64_t cap);
+
+/* ---- coordinate side channel (row f1; HOST functions, synchronous) --------------------------
+ * CoordinateCoder.encode / decode -- coder.py:17-36 (gpcc.py:6-36 -> external tmc3 subprocess).
+ * In-process lossless octree coder of an int32 [n][3] point SET (non-negative coordinates
+ * < 2^21; duplicates collapse; the decoder returns Morton order).  Own stream format ("PCO1"),
+ * not G-PCC: see csrc/octree_coder.cpp.  encode returns the byte count (cap >= 9 + 8 n is
+ * always enough); decode with coords_host == NULL returns the point count. */
+int64_t pcgc_octree_encode_host(const int32_t *coords_host, int64_t n, uint8_t *out_host, int64_t cap);
+int64_t pcgc_octree_decode_host(const uint8_t *in_host, int64_t len, int32_t *coords_host, int64_t cap_rows);
 
 #ifdef __cplusplus
 }

@@ -186,5 +186,14 @@ def decode(sd, stream, rho=1.0, record=None):
     return coords, cls_list
 
 
+def scale_coords(coords3: np.ndarray, factor: float) -> np.ndarray:
+    """``scale_sparse_tensor`` (``data_utils.py:112-118``; ``coder.py:149-152,166-167``): float32 multiply,
+    ``torch.round`` (half to even), int cast, then the coordinate-map insertion of ``ME.SparseTensor`` collapses
+    duplicates (first seen kept, Appendix A.2).  int [N,3] -> int32 [M,3]."""
+    c = (torch.from_numpy(np.asarray(coords3, dtype=np.int32)) * factor).round().int().numpy()
+    c4 = np.concatenate([np.zeros((len(c), 1), dtype=np.int32), c], axis=1)
+    return np.ascontiguousarray(S.unique_coords(c4)[0][:, 1:])
+
+
 def stream_bits(stream) -> int:
     return 8 * (len(stream["F"]) + len(stream["H"]) + len(stream["num_points"]))

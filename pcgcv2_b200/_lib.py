@@ -34,6 +34,7 @@ SIGNATURES = {
     "pcgc_last_error": (ctypes.c_char_p, []),
     "pcgc_launch_count": (ctypes.c_uint64, []),
     "pcgc_pack_keys": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p]),
+    "pcgc_scale_coords": (ctypes.c_int, [c_p, c_i64, ctypes.c_float, c_p, c_p]),
     "pcgc_unpack_keys": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p]),
     "pcgc_hash_capacity": (c_i64, [c_i64]),
     "pcgc_hash_build": (ctypes.c_int, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p]),
@@ -101,6 +102,11 @@ SIGNATURES = {
     "pcgc_rc_decode_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
     "pcgc_rc_encode_u16_host": (c_i64, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
     "pcgc_rc_decode_u16_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
+    "pcgc_ply_count_lines_host": (c_i64, [c_p, c_i64]),
+    "pcgc_ply_parse_ascii_host": (c_i64, [c_p, c_i64, c_p, c_i64]),
+    "pcgc_ply_format_ascii_host": (c_i64, [c_p, c_i64, c_p, c_i64]),
+    "pcgc_octree_encode_host": (c_i64, [c_p, c_i64, c_p, c_i64]),
+    "pcgc_octree_decode_host": (c_i64, [c_p, c_i64, c_p, c_i64]),
 }
 
 class IrnArgs(ctypes.Structure):

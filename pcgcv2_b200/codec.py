@@ -4,9 +4,10 @@
 network, sorts the bottleneck into the canonical symbol order, quantises and range-codes the
 features; ``decode`` inverts it and runs the synthesis network with top-k pruning.  The byte
 layouts of ``_F.bin`` / ``_H.bin`` / ``_num_points.bin`` are the reference's (coder.py:49-55,
-85-87).  The stride-8 coordinate side channel is returned as an int32
-array: the reference pipes it through the external ``tmc3`` binary (coder.py:23-36), which is
-outside the hot path.
+85-87).  The stride-8 coordinate side channel (``_C.bin``, coder.py:23-36)
+is produced by a pluggable coordinate coder (``coords_coder.py``): the in-process octree coder by
+default, or the reference's external ``tmc3`` for byte-identical G-PCC streams; it runs on a side
+thread while this thread range-codes the features.
 
 Unlike the per-operator shim, the pipeline keeps every coordinate set in ascending Morton-key
 order (one radix sort of the input; stride-2 parents, 8-child expansion and stable pruning all
@@ -21,7 +22,11 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
+from concurrent.futures import ThreadPoolExecutor
+
 from . import _lib, ops
+from .coords_coder import OctreeCoordinateCoder
+from .entropy_host import HostTable
 
 
 @dataclass
@@ -30,11 +35,13 @@ class Stream:
     F: bytes
     H: bytes
     num_points: bytes
-    coords: np.ndarray                  # int32 [N3, 3], stride-8 coordinates / 8, canonical order (-> tmc3 in the reference)
+    coords: np.ndarray                  # int32 [N3, 3], stride-8 coordinates / 8, canonical order (what C encodes)
     stats: dict = field(default_factory=dict)
+    C: bytes | None = None              # the coded coordinates (`_C.bin`, coder.py:23-29); None: no coordinate coder configured
 
     def bits(self, coords_bits: int = 0) -> int:
-        return 8 * (len(self.F) + len(self.H) + len(self.num_points)) + coords_bits
+        """total stream size in bits: the four files of coder.py:169-170 (``coords_bits`` stands in for C when it is absent)."""
+        return 8 * (len(self.F) + len(self.H) + len(self.num_points)) + (8 * len(self.C) if self.C is not None else coords_bits)
 
 
 class _Level:
@@ -85,14 +92,26 @@ _FULL = _FullOctets()            # "a full-octet level" for kernel-routing quest
 
 
 class Codec:
-    def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True, use_h2=True, fuse_irn=True):
+    def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True, use_h2=True, fuse_irn=True,
+                 coords_coder="octree"):
+        """``coords_coder``: "octree" (in-process, default), None (hand the coordinates over raw, no ``Stream.C``) or any
+        object with ``encode(int32 [n,3]) -> bytes`` / ``decode(bytes) -> int32 [n,3]`` (e.g. ``Tmc3CoordinateCoder``)."""
+        self.coords_coder = OctreeCoordinateCoder() if coords_coder == "octree" else coords_coder
+        self._side = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pcgc-coords") if self.coords_coder is not None else None
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("pcgcv2_b200.Codec runs on a CUDA device only (there is no CPU path)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.device):             # weight packing launches on THIS device's current stream
+            self._init(state_dict, use_tensor_cores, use_octet_kernels, use_h2, fuse_irn)
+
+    def _init(self, state_dict, use_tensor_cores, use_octet_kernels, use_h2, fuse_irn):
         self.w = {k: v.detach().float().contiguous().to(self.device) for k, v in state_dict.items()
                   if k.startswith(("encoder.", "decoder."))}
         g = lambda name: [state_dict[f"entropy_bottleneck.{name}.{i}"] for i in range(4)]
         self.eb_params = ops.pack_eb_params(g("_matrices"), g("_biases"), g("_factors"), self.device)
+        self.eb_host = HostTable(g("_matrices"), g("_biases"), g("_factors"))       # the range coder's table is host data
         self.channels = self.eb_params.shape[0]
         # k=3 weights pre-packed for the tensor-core kernel where one exists (cin >= 8)
         self.packed = {}
@@ -145,6 +164,7 @@ class Codec:
         self._pinned = {}               # reusable pinned host staging buffers (decoded coordinates, symbols, flags)
         self._tables = {}               # (lo, hi) -> host CDF table
         self._dedupe_next = False
+        self.keep_bottleneck = False    # True: Stream.stats["y_F"] = the float bottleneck [N3, 8] in symbol order (parity tests)
         self.record = None              # set to a dict to capture per-layer activations (parity tests)
         self.probe = {}                 # layer name -> list of (start, end) CUDA event pairs (bench.py roofline)
 
@@ -435,6 +455,15 @@ class Codec:
         finally:
             self._h2_on = on
 
+    def scale(self, coords, factor: float) -> torch.Tensor:
+        """``scale_sparse_tensor`` (data_utils.py:112-118; coder.py:149-152,166-167) on the device: int32 [N,3] -> the
+        scaled, rounded and de-duplicated voxel set, int32 [M,3] (Morton order), on the device."""
+        with torch.cuda.device(self.device), torch.no_grad(), ops.stream_scope():
+            c = torch.as_tensor(coords, dtype=torch.int32).to(self.device, non_blocking=True)
+            c = ops.scale_coords(c[:, -3:].contiguous(), factor)
+            keys, _ = ops.argsort_u64(ops.pack_keys(torch.nn.functional.pad(c, (1, 0)), 1))
+            return ops.unpack_keys(torch.unique_consecutive(keys), 1)[:, 1:].contiguous()
+
     def encode(self, coords) -> Stream:
         """coords: int32 [N,3] (or [N,4] with the batch column; batch 0 only) host array or tensor."""
         st = self._encode(coords)
@@ -448,13 +477,18 @@ class Codec:
         return out if out is not None else self._without_h2(self._decode, stream, rho, to_host)
 
     def _host_table(self, lo: int, hi: int) -> np.ndarray:
-        """uint16-bit CDF table [C, L+1] of the symbol range on the host: a pure function of the model and (lo, hi),
-        computed on the device once (entropy_model.py:151-171) and kept."""
+        """uint16 CDF table [C, L+1] of the symbol range: a pure function of the model and (lo, hi), built once per range
+        on the host with the reference's own float32 operator sequence (entropy_host.py; entropy_model.py:151-171 runs on
+        the CPU too, coder.py:44) and converted like torchac does (Appendix B.1), so that ``F`` is byte-identical to the
+        reference's for identical symbols.  Cached: after the first frame of a symbol range no table work is left."""
         t = self._tables.get((lo, hi))
         if t is None:
             if len(self._tables) > 64:
                 self._tables.clear()
-            t = self._tables[(lo, hi)] = ops.eb_cdf_table(self.eb_params, lo, hi)[1].cpu().numpy()
+            cdf = self.eb_host.cdf_float(lo, hi)
+            lp = cdf.shape[1]
+            scaled = np.round(cdf * np.float32(65536 - (lp - 1)))                       # float32 multiply, half-to-even
+            t = self._tables[(lo, hi)] = (scaled.astype(np.int64) + np.arange(lp)).astype(np.uint16)
         return t
 
     def _staging(self, name, shape, dtype):
@@ -466,11 +500,11 @@ class Codec:
         return buf[:n].view(shape)
 
     def _encode(self, coords, dedupe=False):
-        with torch.no_grad(), ops.stream_scope():
+        with torch.cuda.device(self.device), torch.no_grad(), ops.stream_scope():
             return self._encode_pass(coords, dedupe)
 
     def _decode(self, stream: Stream, rho: float = 1.0, to_host: bool = True):
-        with torch.no_grad(), ops.stream_scope():
+        with torch.cuda.device(self.device), torch.no_grad(), ops.stream_scope():
             return self._decode_pass(stream, rho, to_host)
 
     def _encode_pass(self, coords, dedupe=False):
@@ -493,29 +527,46 @@ class Codec:
         torch.cuda.current_stream().synchronize()
         lo, hi, over, has_dup = flags_h.tolist()
         if has_dup:
+            if over:
+                self._overflow.zero_()                                    # the deduplicated re-run decides for itself
             return "dup"
         if over and self._h2_on:
             self._overflow.zero_()
             self.h2_fallbacks += 1
             return "h2"
+        c3_np = c3_h.numpy().copy()
+        y_keep = y.cpu().numpy() if self.keep_bottleneck else None
+        c_job = self._side.submit(self.coords_coder.encode, c3_np) if self._side is not None else None   # overlaps the range coder
         f_bytes = ops.rc_encode_u16(self._host_table(lo, hi), sym_h.numpy())
         h_bytes = (np.array(y.shape, dtype=np.int32).tobytes() + np.array(1, dtype=np.int8).tobytes() +
                    np.array([lo], dtype=np.float32).tobytes() + np.array([hi], dtype=np.float32).tobytes())
         return Stream(F=f_bytes, H=h_bytes, num_points=np.array(num_points, dtype=np.int32).tobytes(),
-                      coords=c3_h.numpy().copy(), stats={"N": num_points, "sym_range": (lo, hi)})
+                      coords=c3_np, stats={"N": num_points, "sym_range": (lo, hi), **({} if y_keep is None else {"y_F": y_keep})},
+                      C=None if c_job is None else c_job.result())
 
     def _decode_pass(self, stream: Stream, rho: float = 1.0, to_host: bool = True):
         shape = np.frombuffer(stream.H[:8], dtype=np.int32)
         lo = int(np.frombuffer(stream.H[9:13], dtype=np.float32)[0])
         hi = int(np.frombuffer(stream.H[13:17], dtype=np.float32)[0])
         n3, ch = int(shape[0]), int(shape[1])
+        sym_h = self._staging("sym_in", (n3, ch), torch.int16)
+        if stream.C is not None:                                          # coordinates come out of the stream (coder.py:95-96):
+            if self.coords_coder is None:                                 # decoded on the side thread while this one decodes F
+                raise ValueError("the stream carries coded coordinates but this Codec has no coordinate coder")
+            c_job = self._side.submit(self.coords_coder.decode, stream.C)
+            ops.rc_decode_u16(self._host_table(lo, hi), stream.F, n3 * ch, out=sym_h.numpy().reshape(-1))
+            coords_in = c_job.result()
+            if coords_in.shape[0] != n3:
+                raise ValueError(f"coordinate stream holds {coords_in.shape[0]} points, header says {n3}")
+        else:
+            coords_in = stream.coords
         c3_h = self._staging("c3_in", (n3, 3), torch.int32)
-        c3_h.copy_(torch.as_tensor(stream.coords, dtype=torch.int32))
+        c3_h.copy_(torch.as_tensor(coords_in, dtype=torch.int32))
         c3 = c3_h.to(self.device, non_blocking=True)
         c3 = c3[self._canonical_order(c3)]                               # coder.py:97-99 (runs while the host decodes the symbols)
         keys = ops.pack_keys(torch.nn.functional.pad(c3 * 8, (1, 0)), 8)
-        sym_h = self._staging("sym_in", (n3, ch), torch.int16)
-        ops.rc_decode_u16(self._host_table(lo, hi), stream.F, n3 * ch, out=sym_h.numpy().reshape(-1))
+        if stream.C is None:
+            ops.rc_decode_u16(self._host_table(lo, hi), stream.F, n3 * ch, out=sym_h.numpy().reshape(-1))
         y = sym_h.to(self.device, non_blocking=True).float() + float(lo)
         keys, order = ops.argsort_u64(keys)                              # Morton order for the synthesis network
         level3 = _Level(keys, 8)

@@ -63,7 +63,7 @@ static __global__ void split_h2_kernel(const float *__restrict__ in, int in_ld, 
         float4 v;
         if (vec_ok) v = __ldg(reinterpret_cast<const float4 *>(src));
         else v = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
-        over |= fabsf(v.x) > kH2Limit || fabsf(v.y) > kH2Limit || fabsf(v.z) > kH2Limit || fabsf(v.w) > kH2Limit;
+        over |= !(fabsf(v.x) <= kH2Limit) || !(fabsf(v.y) <= kH2Limit) || !(fabsf(v.z) <= kH2Limit) || !(fabsf(v.w) <= kH2Limit);
         uint4 o;
         split_pair_h2(v.x, v.y, o.x, o.z);
         split_pair_h2(v.z, v.w, o.y, o.w);
@@ -173,7 +173,7 @@ struct H2Epilogue {
         if (flags & PCGC_EPI_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
         if (out) *reinterpret_cast<float2 *>(out + row * out_ld + co) = make_float2(v0, v1);
         if (out_h2) {
-            over |= fabsf(v0) > kH2Limit || fabsf(v1) > kH2Limit;
+            over |= !(fabsf(v0) <= kH2Limit) || !(fabsf(v1) <= kH2Limit);
             uint32_t hi, lo;
             split_pair_h2(v0, v1, hi, lo);
             uint32_t *dst = out_h2 + row * out_h2_ld + (co & ~3) + ((co >> 1) & 1);

@@ -150,8 +150,8 @@ __device__ __forceinline__ void finish_row(float (&acc)[COUT], int l, bool valid
                         uint4 q;
                         split_pair_h2(acc[i], acc[i + 1], q.x, q.z);
                         split_pair_h2(acc[i + 2], acc[i + 3], q.y, q.w);
-                        *over |= fabsf(acc[i]) > kH2Limit || fabsf(acc[i + 1]) > kH2Limit || fabsf(acc[i + 2]) > kH2Limit ||
-                                 fabsf(acc[i + 3]) > kH2Limit;
+                        *over |= !(fabsf(acc[i]) <= kH2Limit) || !(fabsf(acc[i + 1]) <= kH2Limit) || !(fabsf(acc[i + 2]) <= kH2Limit) ||
+                                 !(fabsf(acc[i + 3]) <= kH2Limit);
                         *reinterpret_cast<uint4 *>(oh + base + i) = q;
                     }
                 }
@@ -160,7 +160,7 @@ __device__ __forceinline__ void finish_row(float (&acc)[COUT], int l, bool valid
                 split_pair_h2(acc[0], acc[1], hi, lo);
                 const uint32_t phi = __shfl_xor_sync(0xffffffffu, hi, 1 << R::AS), plo = __shfl_xor_sync(0xffffffffu, lo, 1 << R::AS);
                 if (store) {
-                    *over |= fabsf(acc[0]) > kH2Limit || fabsf(acc[1]) > kH2Limit;
+                    *over |= !(fabsf(acc[0]) <= kH2Limit) || !(fabsf(acc[1]) <= kH2Limit);
                     if ((base & 2) == 0) *reinterpret_cast<uint4 *>(oh + base) = make_uint4(hi, phi, lo, plo);
                 }
             }

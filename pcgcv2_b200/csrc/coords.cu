@@ -33,6 +33,12 @@ __global__ void unpack_keys_kernel(const uint64_t *__restrict__ keys, int64_t n,
     }
 }
 
+// scale_sparse_tensor (data_utils.py:112-118): float32 multiply, round half to even (torch.round), int cast
+__global__ void scale_coords_kernel(const int32_t *__restrict__ in, int64_t count, float factor, int32_t *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __float2int_rn(__fmul_rn((float)in[i], factor));
+}
+
 // ---- hash table ---------------------------------------------------------------------------
 __global__ void hash_clear_kernel(uint64_t *__restrict__ tkeys, int32_t *__restrict__ tvals, int64_t cap) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
@@ -228,6 +234,13 @@ int pcgc_unpack_keys(const uint64_t *keys, int64_t n, int32_t tensor_stride, int
     PCGC_REQUIRE(((uintptr_t)coords & 15) == 0, "pcgc_unpack_keys: coords must be 16-byte aligned");
     unpack_keys_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(keys, n, tensor_stride, (int4 *)coords);
     return check_launch("unpack_keys");
+}
+
+int pcgc_scale_coords(const int32_t *coords, int64_t count, float factor, int32_t *out, void *stream) {
+    PCGC_REQUIRE(count >= 0, "pcgc_scale_coords: bad count");
+    if (count == 0) return PCGC_OK;
+    scale_coords_kernel<<<grid_for(count, 256, 8), 256, 0, (cudaStream_t)stream>>>(coords, count, factor, out);
+    return check_launch("scale_coords");
 }
 
 int64_t pcgc_hash_capacity(int64_t n) {

@@ -188,20 +188,55 @@ eb_likelihood_bwd_kernel(const float *__restrict__ values, int64_t total, int ch
     }
 }
 
-// one block per channel: pmf over the symbol grid, sequential cumsum (double accumulator, as the
-// reference's CPU torch.cumsum), clamp, and the torchac integer table.
+// ---- the range coder's table (entropy_model.py:151-171 + torchac's float -> 16-bit conversion, Appendix B.1) ----------
+// An arithmetic-coded stream desynchronises when ONE table entry differs by one count between encoder and decoder, so
+// the table is not evaluated with the fast float32 intrinsics of the likelihood kernel above: every transcendental
+// (softplus, tanh, sigmoid) is evaluated in float64 and the likelihood is rounded to float32 ONCE, then clamped, summed
+// in a float64 accumulator (the reference's CPU torch.cumsum accumulates float32 rows in double), rounded to float32,
+// clamped to 1 and converted exactly like torchac does (float32 multiply, round-half-even, + arange).  This reproduces
+// the reference-generated golden tables exactly (tests/test_ops_gpu.py); the reference's own float32 CPU evaluation
+// still differs from the correctly rounded value in ~0.1 % of the entries over all seven shipped checkpoints, which is
+// why Codec builds the table it codes with on the host with the reference's own operator sequence (codec.py).
+__device__ __forceinline__ double softplus_d(double x) { return x > 20.0 ? x : log1p(exp(x)); }
+__device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+__device__ double logits_cumulative_d(const double *__restrict__ p, double x) {
+    double h[3], g[3];
+    for (int j = 0; j < 3; ++j) {
+        const double v = p[M0 + j] * x + p[B0 + j];
+        h[j] = v + p[F0 + j] * tanh(v);
+    }
+    for (int j = 0; j < 3; ++j) {
+        const double v = p[M1 + 3 * j] * h[0] + p[M1 + 3 * j + 1] * h[1] + p[M1 + 3 * j + 2] * h[2] + p[B1 + j];
+        g[j] = v + p[F1 + j] * tanh(v);
+    }
+    for (int j = 0; j < 3; ++j) {
+        const double v = p[M2 + 3 * j] * g[0] + p[M2 + 3 * j + 1] * g[1] + p[M2 + 3 * j + 2] * g[2] + p[B2 + j];
+        h[j] = v + p[F2 + j] * tanh(v);
+    }
+    const double v = p[M3] * h[0] + p[M3 + 1] * h[1] + p[M3 + 2] * h[2] + p[B3];
+    return v + p[F3] * tanh(v);
+}
+
+// one block per channel
 __global__ void eb_cdf_table_kernel(const float *__restrict__ raw, int channels, int min_v, int L,
                                     float *__restrict__ cdf_float, uint16_t *__restrict__ cdf_u16) {
-    extern __shared__ float sm[];
-    float *tp = sm;                 // [PPC]
-    float *pmf = sm + PPC;          // [L]
+    extern __shared__ double smd[];
+    double *tp = smd;                                   // [PPC] transformed parameters, float64
+    float *pmf = reinterpret_cast<float *>(smd + PPC);  // [L]
     const int c = blockIdx.x;
     for (int i = threadIdx.x; i < PPC; i += blockDim.x) {
-        const float v = raw[c * PPC + i];
-        tp[i] = i < B0 ? softplus_f(v) : (i < F0 ? v : (i < 44 ? tanhf(v) : 0.f));
+        const double v = (double)raw[c * PPC + i];
+        tp[i] = i < B0 ? softplus_d(v) : (i < F0 ? v : (i < 44 ? tanh(v) : 0.0));
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < L; j += blockDim.x) pmf[j] = fmaxf(likelihood_at(tp, (float)(min_v + j)), 1e-9f);
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const double x = (double)(min_v + j);
+        const double lower = logits_cumulative_d(tp, x - 0.5), upper = logits_cumulative_d(tp, x + 0.5);
+        const double sum = lower + upper;
+        const double s = sum > 0.0 ? -1.0 : (sum < 0.0 ? 1.0 : 0.0);
+        pmf[j] = fmaxf((float)fabs(sigmoid_d(s * upper) - sigmoid_d(s * lower)), 1e-9f);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         const int Lp = L + 1;
@@ -271,7 +306,7 @@ int pcgc_eb_cdf_table(const float *params, int32_t channels, int32_t min_v, int3
                       uint16_t *cdf_u16, void *stream) {
     const int64_t L = (int64_t)max_v - min_v + 1;
     PCGC_REQUIRE(channels >= 1 && L >= 1 && L <= 8192, "pcgc_eb_cdf_table: bad symbol range [%d, %d]", min_v, max_v);
-    eb_cdf_table_kernel<<<channels, 128, sizeof(float) * (PPC + L), (cudaStream_t)stream>>>(params, channels, min_v, (int)L,
+    eb_cdf_table_kernel<<<channels, 128, sizeof(double) * PPC + sizeof(float) * L, (cudaStream_t)stream>>>(params, channels, min_v, (int)L,
                                                                                           cdf_float, cdf_u16);
     return check_launch("eb_cdf_table");
 }

@@ -72,6 +72,18 @@ def pack_keys(coords: torch.Tensor, tensor_stride: int) -> torch.Tensor:
     return keys
 
 
+def scale_coords(coords: torch.Tensor, factor: float) -> torch.Tensor:
+    """int32 coordinate values -> round_half_even(float32(v) * float32(factor)) (scale_sparse_tensor, data_utils.py:112-118);
+    duplicates are NOT removed here."""
+    _need_cuda(coords)
+    if coords.dtype != torch.int32:
+        raise ValueError("coordinates must be int32")
+    coords = coords.contiguous()
+    out = torch.empty_like(coords)
+    check(_lib.lib().pcgc_scale_coords(_p(coords), coords.numel(), float(factor), _p(out), _stream()), "pcgc_scale_coords")
+    return out
+
+
 def unpack_keys(keys: torch.Tensor, tensor_stride: int) -> torch.Tensor:
     n = keys.shape[0]
     coords = torch.empty((n, 4), dtype=torch.int32, device=keys.device)
@@ -751,3 +763,27 @@ def rc_decode_u16(table: np.ndarray, data: bytes, n_sym: int, out: np.ndarray | 
     check(_lib.lib().pcgc_rc_decode_u16_host(table.ctypes.data, T, lp, buf.ctypes.data if buf.size else None, buf.size,
                                              out.ctypes.data, n_sym), "pcgc_rc_decode_u16_host")
     return out
+
+
+# ------------------------------------------------------------------ ASCII PLY geometry I/O (host, row f2)
+
+def ply_read_ascii(path, pinned=False) -> torch.Tensor:
+    """ASCII PLY file -> int32 [n, 3] CPU tensor (pinned on request, so that ``.to(device, non_blocking=True)`` is one DMA).
+    Line semantics of the reference's read_ply_ascii_geo (data_utils.py:19-34): see csrc/ply.cpp."""
+    text = np.fromfile(path, dtype=np.uint8)
+    L = _lib.lib()
+    cap = check(L.pcgc_ply_count_lines_host(text.ctypes.data if text.size else None, text.size), "pcgc_ply_count_lines_host") if text.size else 0
+    out = torch.empty((max(cap, 1), 3), dtype=torch.int32, pin_memory=bool(pinned))
+    n = check(L.pcgc_ply_parse_ascii_host(text.ctypes.data, text.size, out.data_ptr(), cap), "pcgc_ply_parse_ascii_host") if text.size else 0
+    return out[:n]
+
+
+def ply_write_ascii(path, coords) -> int:
+    """int [n, 3] host coordinates -> ASCII PLY file in the reference's layout (data_utils.py:36-48); returns the byte count."""
+    c = np.ascontiguousarray(np.asarray(coords.cpu() if isinstance(coords, torch.Tensor) else coords).astype(np.int32)).reshape(-1, 3)
+    buf = np.empty(160 + 36 * c.shape[0], dtype=np.uint8)
+    n = check(_lib.lib().pcgc_ply_format_ascii_host(c.ctypes.data if c.size else None, c.shape[0], buf.ctypes.data, buf.size),
+              "pcgc_ply_format_ascii_host")
+    with open(path, "wb") as f:
+        f.write(memoryview(buf[:n]))
+    return int(n)

@@ -80,6 +80,9 @@ class FramePipeline:
             results[idx] = (st, out)
         for s in self.streams:
             cur.wait_stream(s)
+        for r in results:                                # device results were allocated on a worker's stream: tell the caching
+            if r is not None and isinstance(r[1], torch.Tensor) and r[1].is_cuda:   # allocator the caller's stream uses them too
+                r[1].record_stream(cur)
         if err is not None:
             raise err
         return results

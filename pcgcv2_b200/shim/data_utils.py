@@ -1,8 +1,8 @@
 """Same-named module as the reference's ``data_utils.py`` (imported by its autoencoder.py:4,
 coder.py:7-8, loss.py:4) with the host hops replaced by libpcgc kernels: ``istopk`` (GPU radix
 select instead of D2H + CPU torch.topk, data_utils.py:77-89), ``isin`` (hash probe instead of
-np.isin on the host, :63-75), ``sort_spare_tensor`` (device argsort, :91-101).  PLY I/O is
-vectorised numpy (no per-line Python loop); h5py is optional."""
+np.isin on the host, :63-75), ``sort_spare_tensor`` (device argsort, :91-101).  PLY I/O is one
+native pass over the text (csrc/ply.cpp) into pinned int32 memory; h5py is optional."""
 import os
 
 import numpy as np
@@ -25,27 +25,14 @@ def write_h5_geo(filedir, coords):
 
 
 def read_ply_ascii_geo(filedir):
-    """ASCII PLY -> int [N,3] (first three numeric columns of every all-numeric line)."""
-    with open(filedir) as f:
-        lines = f.read().split('\n')
-    start = 0
-    for i, line in enumerate(lines):
-        if line.strip() == 'end_header':
-            start = i + 1
-            break
-    body = [l for l in lines[start:] if l.strip()]
-    if not body:
-        return np.zeros((0, 3), dtype='int')
-    data = np.loadtxt(body, dtype=np.float64, ndmin=2)
-    return data[:, 0:3].astype('int')
+    """ASCII PLY -> int [N,3]: the first three values of every line whose tokens all parse as floats (the reference's
+    line semantics, data_utils.py:19-34), parsed in one native pass (pcgc_ply_parse_ascii_host, csrc/ply.cpp)."""
+    return _ops.ply_read_ascii(filedir).numpy().astype('int')
 
 
 def write_ply_ascii_geo(filedir, coords):
-    coords = np.asarray(coords).astype('int')
-    with open(filedir, 'w') as f:
-        f.write('ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\n'
-                'property float z\nend_header\n' % coords.shape[0])
-        np.savetxt(f, coords, fmt='%d')
+    """data_utils.py:36-48 without the per-point Python loop (pcgc_ply_format_ascii_host)."""
+    _ops.ply_write_ascii(filedir, np.asarray(coords).astype('int'))
 
 
 def array2vector(array, step):
@@ -85,7 +72,7 @@ def sort_spare_tensor(sparse_tensor):
 
 
 def load_sparse_tensor(filedir, device):
-    coords = torch.tensor(read_ply_ascii_geo(filedir)).int()
+    coords = _ops.ply_read_ascii(filedir, pinned=torch.cuda.is_available())      # int32, pinned: the H2D copy is one DMA
     feats = torch.ones((len(coords), 1)).float()
     coords, feats = ME.utils.sparse_collate([coords], [feats])
     return ME.SparseTensor(features=feats, coordinates=coords, tensor_stride=1, device=device)

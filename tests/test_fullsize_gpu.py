@@ -1,0 +1,101 @@
+"""Parity on BASELINE.json's own configurations at FULL size, against fixtures the CPU oracle produced
+(tests/golden/make_golden_fullsize.py; the oracle needs ~60 s per cloud, the fixtures let the GPU box compare in seconds):
+
+  config 2  synthetic_vox10(seed=0), 795 124 voxels, r3
+  config 3  one of the four jittered frames (seed=1, radii +-10 %), 837 706 voxels
+  config 4  scaling_factor = 0.375, rho = 4 (coder.py:149-152,166-167; data_utils.py:112-118) on the config-2 cloud
+
+Bars (BASELINE.json north_star): bottleneck coordinates / num_points / header bit-exact; bottleneck activations within
+1e-4 relative; total bits (all FOUR files of coder.py:169-170, `_C.bin` through the reference's tmc3) within 1e-4
+relative -- in fact byte-identical whenever the rounded symbols agree, which they do on these clouds; decoded voxel set
+equal to the oracle's; D1 PSNR through the reference's pc_error_d binary within 0.01 dB of the oracle's.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import refbin
+from pcgcv2_b200 import synth
+from pcgcv2_b200.codec import Codec
+from pcgcv2_b200.coords_coder import OctreeCoordinateCoder, Tmc3CoordinateCoder
+from util import GOLDEN, canon, load_ckpt, octree_unpack
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "vox10_seed0": dict(cloud=dict(seed=0), res=1024),
+    "vox10_seed1_jitter": dict(cloud=dict(seed=1, jitter=0.1), res=1024),
+    "vox10_seed0_scale0375_rho4": dict(cloud=dict(seed=0), res=1024, scaling_factor=0.375, rho=4.0),
+}
+
+
+@pytest.fixture(scope="module")
+def r3():
+    torch.set_flush_denormal(True)
+    return load_ckpt("r3")
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fullsize_config_matches_oracle_fixture(r3, case):
+    cfg, g = CASES[case], np.load(os.path.join(GOLDEN, f"oracle_{case}.npz"))
+    sf, rho, res = cfg.get("scaling_factor", 1.0), cfg.get("rho", 1.0), cfg["res"]
+    pts = synth.synthetic_vox10(**cfg["cloud"])
+    assert len(pts) == int(g["n_in"])
+    have_bins = refbin.available()
+    codec = Codec(r3, coords_coder=Tmc3CoordinateCoder(refbin.TMC3) if have_bins else "octree")
+    codec.keep_bottleneck = True
+    x_in = codec.scale(pts, sf) if sf != 1.0 else pts                      # coder.py:149-152
+    assert len(x_in) == int(g["n_coded"])
+    st = codec.encode(x_in)
+    # ---- integer / index work: bit-exact
+    assert (st.coords == g["C_coords"].astype(np.int32)).all(), "bottleneck coordinates (canonical order)"
+    assert st.num_points == g["num_points"].tobytes() and st.H == g["H"].tobytes()
+    # ---- activations at the bottleneck (the product of all 41 analysis layers): 1e-4 relative
+    y, y_ref = st.stats["y_F"], g["y_F"]
+    err = float(np.abs(y - y_ref).max() / np.abs(y_ref).max())
+    assert err < 1e-4, f"bottleneck activations: relative error {err:.2e}"
+    flips = int((np.round(y) != np.round(y_ref)).sum())                     # a symbol flips only within ~1e-5 of a .5 boundary
+    # ---- bits: F byte-identical when the symbols agree; C byte count identical through the same tmc3
+    if flips == 0:
+        assert st.F == g["F"].tobytes(), "feature bitstream differs from the oracle's although the symbols agree"
+    ref_bits = 8 * (len(g["F"]) + len(g["H"]) + len(g["num_points"]) + int(g["C_bytes"]))
+    if have_bins:
+        assert len(st.C) == int(g["C_bytes"]), "tmc3 coordinate stream size"
+        assert abs(st.bits() - ref_bits) <= 1e-4 * ref_bits + 8 * flips, (st.bits(), ref_bits, flips)
+    else:
+        assert abs(8 * len(st.F) - 8 * len(g["F"])) <= 1e-4 * ref_bits + 8 * flips
+    # ---- decode the ORACLE's stream (isolates the synthesis side) and our own stream
+    dec_ref = octree_unpack(g["dec_root"], [g["dec_occ0"], g["dec_occ1"], g["dec_occ2"]])
+    assert len(dec_ref) == int(g["n_dec"])
+    dec = codec.decode(st, rho=rho, to_host=False)
+    if sf != 1.0:
+        dec = codec.scale(dec, 1.0 / sf)                                    # coder.py:166-167
+    dec = dec.cpu().numpy()
+    a, b = set(map(tuple, dec.tolist())), set(map(tuple, dec_ref.tolist()))
+    diff = len(a ^ b)
+    assert len(dec) == len(dec_ref) and diff <= 2e-5 * len(dec_ref) + 4 * flips, f"decoded set differs in {diff} voxels"
+    if flips == 0:
+        assert diff == 0, f"decoded set differs in {diff} voxels with identical symbols"
+    # ---- D1 through the reference's own metric binary (pc_error.py:44-54)
+    if have_bins:
+        with tempfile.TemporaryDirectory() as tmp:
+            d1 = refbin.pc_error_d1(pts, dec, res, tmp)
+        assert abs(d1 - float(g["d1_psnr"])) < 0.01, (d1, float(g["d1_psnr"]))
+    print(f"{case}: N3 {len(st.coords)} act err {err:.2e} symbol flips {flips} bits {st.bits()} (oracle {ref_bits}) set diff {diff}")
+
+
+def test_codec_stream_carries_coded_coordinates(r3):
+    """f1: Codec.decode consumes the coded coordinates (Stream.C), not the raw hand-over; bits() counts all four parts."""
+    pts = synth.ellipsoid_vox8()
+    codec = Codec(r3)
+    st = codec.encode(pts)
+    assert st.C is not None and st.bits() == 8 * (len(st.F) + len(st.H) + len(st.num_points) + len(st.C))
+    want = codec.decode(st).copy()
+    st.coords = None                                                       # decode must not need the raw coordinates
+    assert (canon(codec.decode(st)) == canon(want)).all()
+    raw = Codec(r3, coords_coder=None)
+    st_raw = raw.encode(pts)
+    assert st_raw.C is None and st_raw.F == st.F and (canon(raw.decode(st_raw)) == canon(want)).all()
