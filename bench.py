@@ -14,9 +14,9 @@ embarrassingly per-cloud, so the only collective is an all-gather of per-rank co
 
 Prints ONE JSON line (rank 0).  ``value`` = Mpoints/s with the input voxels already resident in
 HBM; ``e2e`` = the same through the public API with HOST buffers (pinned int32 coordinates in,
-decoded coordinates copied back).  The G-PCC side channel for the ~14 k stride-8 coordinates is an
-external subprocess in the reference (tmc3) and outside this path: both arms
-hand those coordinates over as a raw int32 array.
+decoded coordinates copied back).  The stream every timed frame produces and consumes has all FOUR parts of
+coder.py:169-170: the stride-8 coordinates are coded in-process by the octree coder (own format; the reference
+spawns tmc3 for this, which ``config.reference_equivalent_wall_ms`` includes) and decoded from the stream again.
 
 ``--impl reference`` times the CPU restatement of the reference path (``oracle/``: MinkowskiEngine
 and torchac are not installable here, so this is a "port", not the reference's own binaries) on a
@@ -89,11 +89,30 @@ def k3_algorithmic_bytes(n, pairs, cin, cout):
     return 4 * (n * cin + n * cout) + 8 * pairs + 4 * 27 * cin * cout
 
 
+def pass_algorithmic_bytes(n, p):
+    """SURVEY.md section 8(d) summed over every layer of one encode + decode.  ``n`` / ``p``: rows and k=3 pairs of the seven
+    coordinate sets {"L0".."L3": analysis levels, "U2","U1","U0": synthesis candidate sets 8 N3 / 8 N2 / 8 N1}.
+    Per conv layer 4 (N_in Cin + N_out Cout) + 8 P + 4 K Cin Cout; kernel-map build 8 N + 24 N + 8 P per set; prune
+    4 C (N_in + N_kept) + 8 (N_in + N_kept) + N_in; top-k 8 N_in.  Channel plan: pcc_model.py:11-12, autoencoder.py:7-57."""
+    conv = lambda nin, nout, pairs, cin, cout, k: 4 * (nin * cin + nout * cout) + 8 * pairs + 4 * k * cin * cout
+    k3 = lambda s, cin, cout: conv(n[s], n[s], p[s], cin, cout, 27)
+    k1 = lambda s, cin, cout: conv(n[s], n[s], n[s], cin, cout, 1)
+    irn = lambda s, c: k3(s, c, c // 4) + k3(s, c // 4, c // 2) + k1(s, c, c // 4) + k3(s, c // 4, c // 4) + k1(s, c // 4, c // 2)
+    total = k3("L0", 1, 16)
+    for lo, hi, cin, cout, nxt in (("L0", "L1", 16, 32, 32), ("L1", "L2", 32, 64, 64), ("L2", "L3", 64, 32, 8)):
+        total += conv(n[lo], n[hi], n[lo], cin, cout, 8) + 3 * irn(hi, cout) + k3(hi, cout, nxt)
+    for src, up, kept, cin, cout in (("L3", "U2", "L2", 8, 64), ("L2", "U1", "L1", 64, 32), ("L1", "U0", "L0", 32, 16)):
+        total += conv(n[src], n[up], n[up], cin, cout, 8) + k3(up, cout, cout) + 3 * irn(up, cout) + k3(up, cout, 1)
+        total += 8 * n[up] + 4 * cout * (n[up] + n[kept]) + 8 * (n[up] + n[kept]) + n[up]
+    total += sum(32 * n[s] + 8 * p[s] for s in n)
+    return total
+
+
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full
-    capture (profiles/r01_roofline_traffic.json), per launch; None if the capture is absent."""
+    capture (profiles/r02_roofline_traffic.json, refreshed per round), per launch; None if the capture is absent."""
     try:
-        return int(json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")))["dram_bytes_per_launch"])
+        return int(json.load(open(os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")))["dram_bytes_per_launch"])
     except (OSError, KeyError, ValueError):
         return None
 

@@ -252,7 +252,8 @@ int pcgc_convT_k2s2_fwd_h2out(const float *in, int32_t in_ld, int64_t n_in, cons
  * (same kernels, same order, same results) without a host round trip per layer.  Layers 0..2 = conv0_0, conv0_1,
  * conv1_1 (k=3); w1/b1 = conv1_0, conv1_2 (k=1, reference layout).  x_h2 / out_h2 may be NULL when no layer needs /
  * the caller does not want the h2 copy.  ws: pcgc_irn_ws_bytes(n, c) bytes of device memory for the temporaries. */
-enum { PCGC_ROUTE_H2_GATHER = 0, PCGC_ROUTE_H2_OCTET = 1, PCGC_ROUTE_TF32_GATHER = 2, PCGC_ROUTE_TF32_OCTET = 3, PCGC_ROUTE_FP32 = 4 };
+enum { PCGC_ROUTE_H2_GATHER = 0, PCGC_ROUTE_H2_OCTET = 1, PCGC_ROUTE_TF32_GATHER = 2, PCGC_ROUTE_TF32_OCTET = 3, PCGC_ROUTE_FP32 = 4,
+       PCGC_ROUTE_WIDE = 5 /* tcgen05 / TMA kernel (pcgc_conv_k3_wide_fwd): h2 features, child map */ };
 typedef struct pcgc_irn_args {
     int64_t n;                      /* rows of the coordinate set */
     int32_t c;                      /* block channels (16, 32, 64) */
@@ -353,6 +354,32 @@ int64_t pcgc_rc_encode_u16_host(const uint16_t *cdf_u16_host, int64_t n_tables, 
                                 const int16_t *sym_host, int64_t n_sym, uint8_t *out_host, int64_t cap);
 int pcgc_rc_decode_u16_host(const uint16_t *cdf_u16_host, int64_t n_tables, int32_t lp,
                             const uint8_t *in_host, int64_t in_len, int16_t *sym_host, int64_t n_sym);
+
+/* ---- k=3 convolution on the 5th-generation tensor cores (row a3, wide layers; csrc/conv_wide.cuh) ----
+ * ME.MinkowskiConvolution(k=3) forward -- autoencoder.py:13,20,35,71,90,109,128,162,174,189,201,216,228 -- for
+ * cin in {8,16,32,64}: tcgen05.mma (kind::f16, accumulators in tensor memory), weight tiles streamed
+ * by TMA bulk copies, h2 feature rows gathered verbatim into the swizzled K-major operand layout.
+ * Same contract as pcgc_conv_k3_h2_fwd (h2 features in, fp32 and/or h2 rows out, fused
+ * bias / residual / ReLU, overflow flag); `packed` comes from pcgc_conv_k3_wide_pack_weights
+ * (pcgc_conv_k3_wide_packed_bytes bytes, 0 = no kernel for the shape; weights pre-scaled by the
+ * power of two `scale`, the epilogue multiplies by inv_scale). */
+size_t pcgc_conv_k3_wide_packed_bytes(int32_t cin, int32_t cout);
+int pcgc_conv_k3_wide_pack_weights(const float *weight, int32_t cin, int32_t cout, float scale, void *packed, void *stream);
+int pcgc_conv_k3_wide_fwd(const uint32_t *feats_h2, int32_t in_ld, const int32_t *nbr, int64_t n, const void *packed,
+                          float inv_scale, const float *bias, int32_t cin, int32_t cout, const float *residual,
+                          int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t flags,
+                          int32_t *overflow, void *stream);
+
+/* ---- D1 point-to-point distortion (row f3) --------------------------------------------------
+ * pc_error(infile1, infile2, res) -- pc_error.py:44-54 (pc_error_d -a A -b B --hausdorff=1
+ * --resolution=res-1), read back at coder.py:181-184.  One direction: for every query voxel the
+ * squared distance to the nearest voxel of the other cloud (given as its hash table AND its key
+ * list), exact.  acc3 (device uint64[3]) receives {sum of squared distances, max squared
+ * distance, number of queries that needed the brute-force pass}; open_list: int32 [n_query]
+ * scratch.  mse = acc3[0] / n_query; D1 PSNR = 10 log10(3 (res-1)^2 / max(mse_AB, mse_BA)). */
+int pcgc_d1_sqdist(const uint64_t *query_keys, int64_t n_query, const uint64_t *table_keys, int64_t cap,
+                   const uint64_t *cloud_keys, int64_t n_cloud, int32_t max_radius, uint64_t *acc3, int32_t *open_list,
+                   void *stream);
 
 /* ---- ASCII PLY geometry I/O (row f2; HOST functions, synchronous) ---------------------------
  * read_ply_ascii_geo / write_ply_ascii_geo -- data_utils.py:19-48 (coder.py:26,33,128,177).

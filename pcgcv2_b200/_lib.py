@@ -64,6 +64,10 @@ SIGNATURES = {
     "pcgc_conv_k3_h2_pack_weights": (ctypes.c_int, [c_p, c_i32, c_i32, ctypes.c_float, c_p, c_p]),
     "pcgc_conv_k3_h2_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, ctypes.c_float, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32,
                                             c_p, c_i32, c_i32, c_p, c_p]),
+    "pcgc_conv_k3_wide_packed_bytes": (c_sz, [c_i32, c_i32]),
+    "pcgc_conv_k3_wide_pack_weights": (ctypes.c_int, [c_p, c_i32, c_i32, ctypes.c_float, c_p, c_p]),
+    "pcgc_conv_k3_wide_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, ctypes.c_float, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32,
+                                              c_p, c_i32, c_i32, c_p, c_p]),
     "pcgc_conv_k3_octet_h2_supported": (ctypes.c_int, [c_i32, c_i32]),
     "pcgc_conv_k3_octet_h2_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, ctypes.c_float, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32,
                                                   c_p, c_i32, c_i32, c_p, c_p]),
@@ -102,6 +106,7 @@ SIGNATURES = {
     "pcgc_rc_decode_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
     "pcgc_rc_encode_u16_host": (c_i64, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
     "pcgc_rc_decode_u16_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
+    "pcgc_d1_sqdist": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i32, c_p, c_p, c_p]),
     "pcgc_ply_count_lines_host": (c_i64, [c_p, c_i64]),
     "pcgc_ply_parse_ascii_host": (c_i64, [c_p, c_i64, c_p, c_i64]),
     "pcgc_ply_format_ascii_host": (c_i64, [c_p, c_i64, c_p, c_i64]),
@@ -117,7 +122,7 @@ class IrnArgs(ctypes.Structure):
                 ("b1", c_p * 2), ("ws", c_p), ("ws_bytes", c_sz), ("overflow", c_p)]
 
 
-ROUTE_H2_GATHER, ROUTE_H2_OCTET, ROUTE_TF32_GATHER, ROUTE_TF32_OCTET, ROUTE_FP32 = range(5)
+ROUTE_H2_GATHER, ROUTE_H2_OCTET, ROUTE_TF32_GATHER, ROUTE_TF32_OCTET, ROUTE_FP32, ROUTE_WIDE = range(6)
 
 _lib = None
 

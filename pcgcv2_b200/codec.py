@@ -17,6 +17,7 @@ leaves the device between layers.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -92,8 +93,10 @@ _FULL = _FullOctets()            # "a full-octet level" for kernel-routing quest
 
 
 class Codec:
+    WIDE_SHAPES = {(64, 64)}            # (cin, cout) of the k=3 layers routed to the tcgen05 / TMA kernel
+
     def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True, use_h2=True, fuse_irn=True,
-                 coords_coder="octree"):
+                 coords_coder="octree", wide_shapes=None):
         """``coords_coder``: "octree" (in-process, default), None (hand the coordinates over raw, no ``Stream.C``) or any
         object with ``encode(int32 [n,3]) -> bytes`` / ``decode(bytes) -> int32 [n,3]`` (e.g. ``Tmc3CoordinateCoder``)."""
         self.coords_coder = OctreeCoordinateCoder() if coords_coder == "octree" else coords_coder
@@ -103,6 +106,11 @@ class Codec:
             raise ValueError("pcgcv2_b200.Codec runs on a CUDA device only (there is no CPU path)")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
+        if wide_shapes is None:
+            env = os.environ.get("PCGC_WIDE_SHAPES")
+            wide_shapes = self.WIDE_SHAPES if env is None else (env if env in ("all", "none") else
+                                                                {tuple(int(v) for v in t.split("x")) for t in env.split(",") if t})
+        self.wide_shapes = wide_shapes          # "all" | "none" | set of (cin, cout): k=3 layers routed to the tcgen05 / TMA kernel
         with torch.cuda.device(self.device):             # weight packing launches on THIS device's current stream
             self._init(state_dict, use_tensor_cores, use_octet_kernels, use_h2, fuse_irn)
 
@@ -146,6 +154,16 @@ class Codec:
                         and v.shape[2] % 16 == 0 and ops.PackedK3H2.supported(v.shape[1], 16)):
                     self.packed_h2_slices[name] = [(ops.PackedK3H2(v[:, :, j:j + 16].contiguous()),
                                                     self.w[name + ".bias"][:, j:j + 16]) for j in range(0, v.shape[2], 16)]
+        # tcgen05 / TMA kernel (csrc/conv_wide.cuh) for the shapes where it beats the mma.sync kernels (tools/bench_wide.py,
+        # profiles/r02_wide_tcgen05.txt); PCGC_WIDE_SHAPES="64x64,32x32" | "all" | "none" overrides the routed set
+        self.packed_wide = {}
+        if use_h2 and use_tensor_cores:
+            for k, v in self.w.items():
+                if k.endswith(".kernel") and v.dim() == 3 and v.shape[0] == 27:
+                    shape = (int(v.shape[1]), int(v.shape[2]))
+                    routed = self.wide_shapes == "all" or (self.wide_shapes != "none" and shape in self.wide_shapes)
+                    if routed and ops.PackedK3Wide.supported(*shape):
+                        self.packed_wide[k[:-len(".kernel")]] = ops.PackedK3Wide(v)
         # k=2 stride-2 / transposed layers on the tensor cores (gather over the 8 child slots / one dense product)
         self.packed_down_h2, self.packed_up_h2 = {}, {}
         if use_h2 and use_tensor_cores:
@@ -186,24 +204,28 @@ class Codec:
         """one k=3 layer.  ``out`` / ``out_h``: column slices to write into (fp32 / h2); ``want_h``: the consumer is an
         h2 kernel, so an h2 producer writes that format in its epilogue (others are split lazily by ``_h``)."""
         aligned = x.f is None or x.f.stride(0) % 4 == 0
-        ph = self.packed_h2.get(name) if self._h2_on else None
+        pwide = self.packed_wide.get(name) if self._h2_on else None
+        ph = self.packed_h2.get(name) if (self._h2_on and pwide is None) else None
         oh = ph if (ph is not None and level.full_octets and self.use_octet and ops.octet_h2_supported(ph.cin, ph.cout)) else None
         if ph is not None and oh is None and not ph.gather:
             ph = None
-        po = self.packed_octet.get(name) if (oh is None and level.full_octets and aligned and x.f is not None) else None
+        po = self.packed_octet.get(name) if (pwide is None and oh is None and level.full_octets and aligned and x.f is not None) else None
         if po is not None:
             ph = None
         pw = self.packed.get(name) if (aligned and x.f is not None) else None
         ev = self.probe.get(name)
-        sl = self.packed_h2_slices.get(name) if (self._h2_on and po is None) else None
+        sl = self.packed_h2_slices.get(name) if (self._h2_on and po is None and pwide is None) else None
         if ev is not None:
             nbr = level.parent.nbr if (po is not None or oh is not None) else level.nbr   # keep the (cached) map build outside the probe
-            if ph is not None:
+            if ph is not None or pwide is not None or sl is not None:
                 self._h(x)
             start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             start.record()
         y = _F()
-        if oh is not None:       # 8-child expansion + pre-split f16 features: halo of h2 rows, LDS.128 -> HMMA.16816
+        if pwide is not None:    # tcgen05.mma over TMA-streamed weight tiles, accumulators in tensor memory
+            y.f, y.h = ops.conv_k3_wide(self._h(x), level.nbr, pwide, self.w[name + ".bias"], residual=residual, relu=relu, out=out,
+                                        out_h2=out_h, want_f32=want_f, want_h2=want_h and pwide.cout % 4 == 0, overflow=self._overflow)
+        elif oh is not None:     # 8-child expansion + pre-split f16 features: halo of h2 rows, LDS.128 -> HMMA.16816
             y.f, y.h = ops.conv_k3_octet_h2(self._h(x), level.parent.nbr, oh, self.w[name + ".bias"], residual=residual, relu=relu,
                                             out=out, out_h2=out_h, want_f32=want_f, want_h2=want_h and oh.cout % 4 == 0,
                                             overflow=self._overflow)
@@ -245,7 +267,9 @@ class Codec:
         return ops.conv_k1(x, w, self.w[name + ".bias"], residual=residual, relu=relu, out=out), None
 
     def _uses_h2(self, name, level):
-        """the layer will run on an h2 kernel (gather or full-octet variant)."""
+        """the layer will run on an h2 kernel (tcgen05, gather or full-octet variant)."""
+        if self._h2_on and name in self.packed_wide:
+            return True
         if self._h2_on and name in self.packed_h2_slices and not (level.full_octets and name in self.packed_octet):
             return True
         if not (self._h2_on and name in self.packed_h2):
@@ -260,6 +284,9 @@ class Codec:
     # ---- one InceptionResNet block per C call (csrc/irn.cpp): same kernels, same order, no Python between the launches
     def _route(self, name, full_octets, aligned=True):
         """(route code, packed weights tensor, inverse weight scale) of one k=3 layer -- the decision ``_k3`` takes."""
+        pwide = self.packed_wide.get(name) if self._h2_on else None
+        if pwide is not None:
+            return _lib.ROUTE_WIDE, pwide.packed, pwide.inv_scale
         ph = self.packed_h2.get(name) if self._h2_on else None
         if ph is not None and full_octets and self.use_octet and ops.octet_h2_supported(ph.cin, ph.cout):
             return _lib.ROUTE_H2_OCTET, ph.packed, ph.inv_scale
@@ -291,9 +318,9 @@ class Codec:
             routes = list(args.route)
             plan = self._irn_plans[key] = {
                 "args": args, "keep": keep,
-                "child_map": any(r in (_lib.ROUTE_H2_GATHER, _lib.ROUTE_TF32_GATHER, _lib.ROUTE_FP32) for r in routes),
+                "child_map": any(r in (_lib.ROUTE_H2_GATHER, _lib.ROUTE_TF32_GATHER, _lib.ROUTE_FP32, _lib.ROUTE_WIDE) for r in routes),
                 "parent_map": any(r in (_lib.ROUTE_H2_OCTET, _lib.ROUTE_TF32_OCTET) for r in routes),
-                "x_h2": routes[0] in (_lib.ROUTE_H2_GATHER, _lib.ROUTE_H2_OCTET)}
+                "x_h2": routes[0] in (_lib.ROUTE_H2_GATHER, _lib.ROUTE_H2_OCTET, _lib.ROUTE_WIDE)}
         return plan
 
     def _irn_fused(self, prefix, x: _F, level) -> _F:

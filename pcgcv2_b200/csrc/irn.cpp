@@ -16,7 +16,7 @@ void set_error(const char *fmt, ...);
 
 namespace {
 
-inline bool h2_route(int r) { return r == PCGC_ROUTE_H2_GATHER || r == PCGC_ROUTE_H2_OCTET; }
+inline bool h2_route(int r) { return r == PCGC_ROUTE_H2_GATHER || r == PCGC_ROUTE_H2_OCTET || r == PCGC_ROUTE_WIDE; }
 
 // one k=3 layer of the block through the kernel its route names
 int run_k3(const pcgc_irn_args *a, int i, const float *in_f, const uint32_t *in_h, int in_ld, int cin, int cout, const float *residual,
@@ -26,6 +26,9 @@ int run_k3(const pcgc_irn_args *a, int i, const float *in_f, const uint32_t *in_
         case PCGC_ROUTE_H2_GATHER:
             return pcgc_conv_k3_h2_fwd(in_h, in_ld, a->nbr, n, (const uint32_t *)a->w3[i], a->inv_scale[i], a->b3[i], cin, cout, residual,
                                        res_ld, out, out_ld, out_h2, out_h2_ld, flags, a->overflow, stream);
+        case PCGC_ROUTE_WIDE:
+            return pcgc_conv_k3_wide_fwd(in_h, in_ld, a->nbr, n, a->w3[i], a->inv_scale[i], a->b3[i], cin, cout, residual, res_ld, out,
+                                         out_ld, out_h2, out_h2_ld, flags, a->overflow, stream);
         case PCGC_ROUTE_H2_OCTET:
             return pcgc_conv_k3_octet_h2_fwd(in_h, in_ld, a->parent_nbr, n_par, (const uint32_t *)a->w3[i], a->inv_scale[i], a->b3[i], cin,
                                              cout, residual, res_ld, out, out_ld, out_h2, out_h2_ld, flags, a->overflow, stream);
@@ -59,7 +62,8 @@ int pcgc_irn_fwd(const pcgc_irn_args *a, void *stream) {
     const int c = a->c, h = c / 2, q = c / 4;
     const bool want_h2 = a->out_h2 != nullptr;
     for (int i = 0; i < 3; ++i) {
-        const bool needs_child_map = a->route[i] == PCGC_ROUTE_H2_GATHER || a->route[i] == PCGC_ROUTE_TF32_GATHER || a->route[i] == PCGC_ROUTE_FP32;
+        const bool needs_child_map = a->route[i] == PCGC_ROUTE_H2_GATHER || a->route[i] == PCGC_ROUTE_TF32_GATHER || a->route[i] == PCGC_ROUTE_FP32 ||
+                                     a->route[i] == PCGC_ROUTE_WIDE;
         if ((needs_child_map && !a->nbr) || (!needs_child_map && (!a->parent_nbr || a->n % 8 != 0)) || !a->w3[i]) {
             pcgc::set_error("pcgc_irn_fwd: layer %d: kernel map or weights missing for route %d", i, a->route[i]);
             return PCGC_ERR_INVALID;

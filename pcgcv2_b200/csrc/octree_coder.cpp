@@ -127,35 +127,61 @@ struct NodeTable {                                           // Morton key -> no
     }
 };
 
-// intra-prediction weights: child j of a node against the node's 26 neighbours, w = 1024 / distance^3
+// intra-prediction weights: child j of a node against the node's 3x3x3 neighbourhood (index (dx+1)*9 + (dy+1)*3 + (dz+1),
+// the centre weighs 0), w = 1024 / distance^3; tab[g][pattern][j] = summed weight of the occupied neighbours of x-plane g
 struct Weights {
-    int32_t w[8][26], total[8];
-    int8_t d[26][3];
+    int32_t w[8][27], total[8];
+    int32_t tab[3][512][8];
     Weights() {
-        int n = 0;
-        for (int dx = -1; dx <= 1; ++dx)
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dz = -1; dz <= 1; ++dz) {
-                    if (!dx && !dy && !dz) continue;
-                    d[n][0] = (int8_t)dx; d[n][1] = (int8_t)dy; d[n][2] = (int8_t)dz;
-                    ++n;
-                }
         for (int j = 0; j < 8; ++j) {
             total[j] = 0;
-            // child centres sit at +-1/4 of the node; all distances below are square roots of k/16 with integer k, and the
-            // weights are rounded from exactly representable inputs: identical on every IEEE-754 host
+            // child centres sit at +-1/4 of the node: every squared distance is k/16 with integer k, the weights are rounded
+            // from exactly representable inputs with correctly rounded IEEE operations -- identical on every host
             const double cx = (j & 1) ? 0.25 : -0.25, cy = (j & 2) ? 0.25 : -0.25, cz = (j & 4) ? 0.25 : -0.25;
-            for (int i = 0; i < 26; ++i) {
-                const double q = (d[i][0] - cx) * (d[i][0] - cx) + (d[i][1] - cy) * (d[i][1] - cy) + (d[i][2] - cz) * (d[i][2] - cz);
+            for (int i = 0; i < 27; ++i) {
+                const int dx = i / 9 - 1, dy = (i / 3) % 3 - 1, dz = i % 3 - 1;
+                if (!dx && !dy && !dz) { w[j][i] = 0; continue; }
+                const double q = (dx - cx) * (dx - cx) + (dy - cy) * (dy - cy) + (dz - cz) * (dz - cz);
                 w[j][i] = (int32_t)std::floor(1024.0 / (q * std::sqrt(q)) + 0.5);
                 total[j] += w[j][i];
             }
         }
+        for (int g = 0; g < 3; ++g)
+            for (int p = 0; p < 512; ++p)
+                for (int j = 0; j < 8; ++j) {
+                    int32_t sum = 0;
+                    for (int b = 0; b < 9; ++b)
+                        if (p >> b & 1) sum += w[j][9 * g + b];
+                    tab[g][p][j] = sum;
+                }
     }
 };
 const Weights &weights() { static const Weights W; return W; }
 
-constexpr int kMaxDepth = 21, kCtxPerLevel = 8 * 8 * 3;
+constexpr int kMaxDepth = 21, kCtxPerLevel = 8 * 8 * 3, kDenseBits = 21;
+
+// occupancy of one tree level: value 0 = empty, 0x100 | child-occupancy byte otherwise (the byte is 0 until the node is coded).
+// Levels of up to 2^21 cells live in a dense grid with a one-cell border (no bounds checks, 27 plain loads per node);
+// deeper levels fall back to a hash table.
+struct LevelMap {
+    bool dense = false;
+    int dim = 0;                                             // dense: cells per axis + 2
+    std::vector<uint16_t> grid;
+    NodeTable table;
+    std::vector<uint16_t> vals;
+    void build(const std::vector<uint64_t> &nodes, int l) {
+        dense = 3 * l <= kDenseBits;
+        if (dense) {
+            dim = (1 << l) + 2;
+            grid.assign((size_t)dim * dim * dim, 0);
+            for (uint64_t k : nodes) grid[index(compact3(k), compact3(k >> 1), compact3(k >> 2))] = 0x100;
+        } else {
+            table.build(nodes);
+            vals.assign(nodes.size(), 0x100);
+        }
+    }
+    inline size_t index(uint32_t x, uint32_t y, uint32_t z) const { return ((size_t)(x + 1) * dim + (y + 1)) * dim + (z + 1); }
+};
 
 // one pass over the tree; CODE(model, bit) either encodes the given bit or returns the decoded one
 template <class Coder>
@@ -163,33 +189,48 @@ int64_t walk(int depth, std::vector<uint64_t> &level, const std::vector<uint64_t
     // level: Morton keys of the occupied nodes of the current level, ascending; starts as the root {0}
     const Weights &W = weights();
     std::vector<Model> models((size_t)depth * kCtxPerLevel);
-    std::vector<uint8_t> occ;                                // child-occupancy byte per node of `level` (filled in order)
     std::vector<uint64_t> next;
-    NodeTable table;
+    LevelMap map;
     for (int l = 0; l < depth; ++l) {
-        table.build(level);
-        occ.assign(level.size(), 0);
+        map.build(level, l);
         next.clear();
         Model *M = models.data() + (size_t)l * kCtxPerLevel;
-        const uint32_t lim = 1u << l;                        // nodes of this level have coordinates in [0, lim)
+        const int64_t lim = (int64_t)1 << l;                 // nodes of this level have coordinates in [0, lim)
         const int shift = 3 * (depth - l - 1);               // leaves >> shift = child-level keys
         size_t leaf_pos = 0;
         for (size_t ni = 0; ni < level.size(); ++ni) {
             const uint64_t key = level[ni];
             const uint32_t x = compact3(key), y = compact3(key >> 1), z = compact3(key >> 2);
-            // (a) occupancy of the 26 neighbours at this level; (b) occupancy bytes of the three lower face neighbours
-            int32_t score[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            uint8_t lower[3] = {0, 0, 0};
-            for (int i = 0; i < 26; ++i) {
-                const int64_t nx = (int64_t)x + W.d[i][0], ny = (int64_t)y + W.d[i][1], nz = (int64_t)z + W.d[i][2];
-                if (nx < 0 || ny < 0 || nz < 0 || nx >= lim || ny >= lim || nz >= lim) continue;
-                const int32_t idx = table.find(morton((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
-                if (idx < 0) continue;
-                for (int j = 0; j < 8; ++j) score[j] += W.w[j][i];
-                if (W.d[i][0] == -1 && !W.d[i][1] && !W.d[i][2]) lower[0] = occ[idx];
-                if (!W.d[i][0] && W.d[i][1] == -1 && !W.d[i][2]) lower[1] = occ[idx];
-                if (!W.d[i][0] && !W.d[i][1] && W.d[i][2] == -1) lower[2] = occ[idx];
+            // (a) occupancy pattern of the 3x3x3 neighbourhood; (b) occupancy bytes of the three lower face neighbours
+            uint32_t pat[3] = {0, 0, 0};
+            uint32_t lower[3] = {0, 0, 0};
+            size_t self = 0;
+            if (map.dense) {
+                self = map.index(x, y, z);
+                const uint16_t *c = map.grid.data() + self;
+                const ptrdiff_t sx = (ptrdiff_t)map.dim * map.dim, sy = map.dim;
+                for (int g = 0; g < 3; ++g) {
+                    const uint16_t *r = c + (g - 1) * sx;
+                    uint32_t p = 0;
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dz = -1; dz <= 1; ++dz) p |= (uint32_t)(r[dy * sy + dz] != 0) << ((dy + 1) * 3 + (dz + 1));
+                    pat[g] = p;
+                }
+                lower[0] = c[-sx] & 0xFF; lower[1] = c[-sy] & 0xFF; lower[2] = c[-1] & 0xFF;
+            } else {
+                for (int i = 0; i < 27; ++i) {
+                    const int dx = i / 9 - 1, dy = (i / 3) % 3 - 1, dz = i % 3 - 1;
+                    const int64_t nx = (int64_t)x + dx, ny = (int64_t)y + dy, nz = (int64_t)z + dz;
+                    if (nx < 0 || ny < 0 || nz < 0 || nx >= lim || ny >= lim || nz >= lim) continue;
+                    const int32_t idx = map.table.find(morton((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
+                    if (idx < 0) continue;
+                    pat[i / 9] |= 1u << (i % 9);
+                    if (i == 4) lower[0] = map.vals[idx] & 0xFF;       // (-1, 0, 0)
+                    if (i == 10) lower[1] = map.vals[idx] & 0xFF;      // (0, -1, 0)
+                    if (i == 12) lower[2] = map.vals[idx] & 0xFF;      // (0, 0, -1)
+                }
             }
+            const int32_t *t0 = W.tab[0][pat[0]], *t1 = W.tab[1][pat[1]], *t2 = W.tab[2][pat[2]];
             uint8_t want = 0;
             if (leaves) {                                    // encoder: this node's true occupancy byte
                 const uint64_t lo = key << 3;
@@ -198,22 +239,23 @@ int64_t walk(int depth, std::vector<uint64_t> &level, const std::vector<uint64_t
                 while (p < leaves->size() && (((*leaves)[p] >> shift) >> 3) == key) { want |= (uint8_t)(1u << (((*leaves)[p] >> shift) & 7)); ++p; }
                 leaf_pos = p;
             }
-            uint8_t byte = 0;
+            uint32_t byte = 0;
             int cnt = 0;
             for (int j = 0; j < 8; ++j) {
                 const int ix = j & 1, iy = (j >> 1) & 1, iz = (j >> 2) & 1;
-                int sb = (int)(((int64_t)score[j] * 16) / W.total[j]);
+                int sb = (int)(((int64_t)(t0[j] + t1[j] + t2[j]) * 16) / W.total[j]);
                 if (sb > 7) sb = 7;
                 const int fx = ix ? (byte >> (j - 1)) & 1 : (lower[0] >> (j + 1)) & 1;     // child at x-1: sibling j-1 / neighbour's child j+1
                 const int fy = iy ? (byte >> (j - 2)) & 1 : (lower[1] >> (j + 2)) & 1;
                 const int fz = iz ? (byte >> (j - 4)) & 1 : (lower[2] >> (j + 4)) & 1;
                 Model &m = M[(sb * 8 + (fx | fy << 1 | fz << 2)) * 3 + (cnt > 2 ? 2 : cnt)];
                 const int bit = code(m, (want >> j) & 1);
-                byte |= (uint8_t)(bit << j);
+                byte |= (uint32_t)bit << j;
                 cnt += bit;
             }
             if (!byte || next.size() > max_nodes) return -1; // corrupt stream: a childless node / more nodes than points
-            occ[ni] = byte;
+            if (map.dense) map.grid[self] = (uint16_t)(0x100 | byte);
+            else map.vals[ni] = (uint16_t)(0x100 | byte);
             for (int j = 0; j < 8; ++j)
                 if (byte >> j & 1) next.push_back(key << 3 | (uint64_t)j);
         }

@@ -230,3 +230,18 @@ def test_irn_block_per_c_call_is_the_same_computation(r3, use_h2):
         assert a.F == b.F and a.H == b.H and (a.coords == b.coords).all() and fused._irn_plans and not plain._irn_plans
         da, db = fused.decode(a, to_host=False), plain.decode(b, to_host=False)
         assert torch.equal(da, db)                                # same rows in the same order
+
+
+def test_tcgen05_routes_give_the_same_stream_and_occupancy(r3):
+    """every k=3 layer that has a tcgen05 / TMA kernel routed to it (wide_shapes="all") == none routed: same bitstream,
+    same decoded set on the KAT cloud; the default routing is a subset of "all" and goes through pcgc_irn_fwd too."""
+    pts = synth.ellipsoid_vox8()
+    every, none, default = Codec(r3, wide_shapes="all"), Codec(r3, wide_shapes="none"), Codec(r3)
+    assert len(every.packed_wide) >= 40 and not none.packed_wide and default.packed_wide
+    a, b, c = every.encode(pts), none.encode(pts), default.encode(pts)
+    assert a.F == b.F == c.F and a.H == b.H and (a.coords == b.coords).all()
+    da, db, dc = every.decode(a), none.decode(b), default.decode(c)
+    assert (canon(da) == canon(db)).all() and (canon(dc) == canon(db)).all()
+    assert every.h2_fallbacks == 0 and default.h2_fallbacks == 0
+    plain = Codec(r3, wide_shapes="all", fuse_irn=False)                 # layer-by-layer == one C call per block
+    assert plain.encode(pts).F == a.F and (canon(plain.decode(a)) == canon(da)).all()

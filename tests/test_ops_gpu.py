@@ -376,6 +376,55 @@ def test_conv_k3_h2_vs_oracle(cin, cout):
         assert _rel_err(got, torch.relu(S.conv_k3(f[:n], cc, 1, w, b))) < H2_TOL
 
 
+WIDE_SHAPES = [(64, 64), (64, 16), (64, 1), (32, 32), (32, 8), (32, 1), (16, 32), (16, 16), (16, 4), (16, 1), (8, 16), (8, 8)]
+
+
+@pytest.mark.parametrize("cin,cout", WIDE_SHAPES)
+def test_conv_k3_wide_tcgen05_vs_oracle(cin, cout):
+    """tcgen05 / TMA k=3 convolution (csrc/conv_wide.cuh) == oracle through both outputs, with the fused residual / ReLU,
+    column-slice outputs, strided inputs, ragged tile tails and fewer tiles than SMs; same bound as the mma.sync h2 kernels."""
+    c = _surface()[:40013]                                        # > 2 tiles per SM: stage and accumulator-buffer reuse
+    keys = _keys(c)
+    nbr = ops.kernel_map_k3(keys, ops.HashTable(keys))
+    g = torch.Generator().manual_seed(cin * 13 + cout)
+    f = torch.randn(len(c), cin, generator=g) * 3.0
+    w = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    b = torch.randn(1, cout, generator=g)
+    ref = S.conv_k3(f, c, 1, w, b)
+    assert ops.PackedK3Wide.supported(cin, cout)
+    pw = ops.PackedK3Wide(w.to(DEV))
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    xh = ops.split_h2(f.to(DEV))
+    got, got_h = ops.conv_k3_wide(xh, nbr, pw, b.to(DEV), want_h2=cout % 4 == 0, overflow=flag)
+    err = _rel_err(got, ref)
+    print(f"wide {cin}->{cout}: rel err {err:.2e}")
+    assert err < H2_TOL
+    if cout % 4 == 0:
+        assert _rel_err(ops.join_h2(got_h), ref) < H2_TOL
+        only_h = ops.conv_k3_wide(xh, nbr, pw, b.to(DEV), want_f32=False, want_h2=True)
+        assert only_h[0] is None and torch.equal(only_h[1], got_h)
+        res = torch.randn(len(c), cout, generator=g)
+        wide = torch.full((len(c), cout + 8), -7.0, device=DEV)
+        wide_h = torch.full((len(c), cout + 8), 5, dtype=torch.int32, device=DEV)
+        ops.conv_k3_wide(xh, nbr, pw, b.to(DEV), residual=res.to(DEV), relu=True, out=wide[:, 4:4 + cout], out_h2=wide_h[:, 4:4 + cout])
+        want = torch.relu(ref + res)
+        assert _rel_err(wide[:, 4:4 + cout], want) < H2_TOL and _rel_err(ops.join_h2(wide_h[:, 4:4 + cout]), want) < H2_TOL
+        assert (wide[:, :4] == -7).all() and (wide[:, 4 + cout:] == -7).all()
+        assert (wide_h[:, :4] == 5).all() and (wide_h[:, 4 + cout:] == 5).all()
+        wide_in = torch.zeros((len(c), cin + 4), dtype=torch.int32, device=DEV)      # strided input rows
+        wide_in[:, 4:] = xh
+        assert _rel_err(ops.conv_k3_wide(wide_in[:, 4:], nbr, pw, b.to(DEV))[0], ref) < H2_TOL
+    assert int(flag.item()) == 0
+    again = ops.conv_k3_wide(xh, nbr, pw, b.to(DEV))[0]
+    assert torch.equal(again, got)                                # deterministic: no atomics, fixed accumulation order
+    for n in (1, 127, 129, 2049):                                 # tile tails, fewer tiles than SMs
+        cc = c[:n]
+        kk = _keys(cc)
+        nb = ops.kernel_map_k3(kk, ops.HashTable(kk))
+        got = ops.conv_k3_wide(ops.split_h2(f[:n].to(DEV)), nb, pw, b.to(DEV), relu=True)[0]
+        assert _rel_err(got, torch.relu(S.conv_k3(f[:n], cc, 1, w, b))) < H2_TOL
+
+
 @pytest.mark.parametrize("cin,cout", [(16, 1), (16, 4), (16, 8), (16, 16), (16, 32), (4, 8), (4, 4)])
 def test_conv_k3_octet_h2_vs_oracle(cin, cout):
     """full-octet h2 kernels (halo of h2 rows in shared memory, parent's map) == oracle on the 8-child expansion;

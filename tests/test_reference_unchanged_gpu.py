@@ -21,12 +21,13 @@ pytestmark = [pytest.mark.gpu,
 
 def _run_reference(sd, pts, tmp_path, res, rho=1.0, scaling_factor=1.0):
     coder = refbin.load_reference_coder()
-    ply = str(tmp_path / "cloud.ply")
+    ply = str(tmp_path / "input_cloud.ply")                                # (CoordinateCoder deletes <prefix>.ply, coder.py:27,34)
     ops.ply_write_ascii(ply, pts)
     x = coder.load_sparse_tensor(ply, coder.device)                        # data_utils.load_sparse_tensor (shim)
     model = coder.PCCModel().to(coder.device)
     model.load_state_dict(refbin.reference_state_dict(sd))                 # strict, coder.py:142
-    prefix = str(tmp_path / "cloud")
+    os.makedirs(str(tmp_path / "output"), exist_ok=True)                   # coder.py:131-134
+    prefix = str(tmp_path / "output" / "cloud")
     c = coder.Coder(model=model, filename=prefix)
     x_in = coder.scale_sparse_tensor(x, factor=scaling_factor) if scaling_factor != 1 else x
     c.encode(x_in)
@@ -36,8 +37,12 @@ def _run_reference(sd, pts, tmp_path, res, rho=1.0, scaling_factor=1.0):
     files = {p: open(prefix + p, "rb").read() for p in ("_C.bin", "_F.bin", "_H.bin", "_num_points.bin")}
     dec = x_dec.C.detach().cpu().numpy()[:, 1:]
     coder.write_ply_ascii_geo(prefix + "_dec.ply", dec)
-    d1 = coder.pc_error(ply, prefix + "_dec.ply", res=res, show=False)["mseF,PSNR (p2point)"][0]
-    return files, dec, float(d1), len(x)
+    metrics = coder.pc_error(ply, prefix + "_dec.ply", res=res, show=False)          # coder.py:181-184
+    assert "mseF,PSNR (p2point)" in metrics, (
+        f"pc_error printed no D1 line for {len(dec)} decoded points; columns {list(metrics.columns)}; "
+        + __import__("subprocess").run([refbin.PC_ERROR, "-a", ply, "-b", prefix + "_dec.ply", "--hausdorff=1", f"--resolution={res - 1}"],
+                                       capture_output=True, text=True).stdout[-600:])
+    return files, dec, float(metrics["mseF,PSNR (p2point)"][0]), len(x)
 
 
 def test_unchanged_reference_coder_on_gpu_matches_oracle_and_codec(tmp_path):
