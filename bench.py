@@ -98,14 +98,14 @@ def pass_algorithmic_bytes(n, p):
     k3 = lambda s, cin, cout: conv(n[s], n[s], p[s], cin, cout, 27)
     k1 = lambda s, cin, cout: conv(n[s], n[s], n[s], cin, cout, 1)
     irn = lambda s, c: k3(s, c, c // 4) + k3(s, c // 4, c // 2) + k1(s, c, c // 4) + k3(s, c // 4, c // 4) + k1(s, c // 4, c // 2)
-    total = k3("L0", 1, 16)
+    convs = k3("L0", 1, 16)
+    other = sum(32 * n[s] + 8 * p[s] for s in n)                       # kernel-map builds
     for lo, hi, cin, cout, nxt in (("L0", "L1", 16, 32, 32), ("L1", "L2", 32, 64, 64), ("L2", "L3", 64, 32, 8)):
-        total += conv(n[lo], n[hi], n[lo], cin, cout, 8) + 3 * irn(hi, cout) + k3(hi, cout, nxt)
+        convs += conv(n[lo], n[hi], n[lo], cin, cout, 8) + 3 * irn(hi, cout) + k3(hi, cout, nxt)
     for src, up, kept, cin, cout in (("L3", "U2", "L2", 8, 64), ("L2", "U1", "L1", 64, 32), ("L1", "U0", "L0", 32, 16)):
-        total += conv(n[src], n[up], n[up], cin, cout, 8) + k3(up, cout, cout) + 3 * irn(up, cout) + k3(up, cout, 1)
-        total += 8 * n[up] + 4 * cout * (n[up] + n[kept]) + 8 * (n[up] + n[kept]) + n[up]
-    total += sum(32 * n[s] + 8 * p[s] for s in n)
-    return total
+        convs += conv(n[src], n[up], n[up], cin, cout, 8) + k3(up, cout, cout) + 3 * irn(up, cout) + k3(up, cout, 1)
+        other += 8 * n[up] + 4 * cout * (n[up] + n[kept]) + 8 * (n[up] + n[kept]) + n[up]      # top-k + prune
+    return convs, convs + other                                         # (the 106 convolutions: SURVEY Appendix C's 8.57 GB; everything)
 
 
 def ncu_traffic_bytes():
@@ -117,6 +117,59 @@ def ncu_traffic_bytes():
         return None
 
 
+def pin_rank_threads(local_rank, local_world):
+    """give every rank of this node its own slice of the host cores: each rank runs `depth` frame threads, `depth` coordinate-coder
+    threads and the main thread, and eight ranks on one shared core set contend (round 1: 0.92 scaling efficiency at 8 GPUs with
+    no collective on the data path)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(local_world, 1)
+        if local_world > 1 and per >= 2:
+            mine = cores[local_rank * per:(local_rank + 1) * per]
+            os.sched_setaffinity(0, mine)
+            return len(mine)
+        return len(cores)
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
+def reference_equivalent_wall(pts, sd, res=1024):
+    """SURVEY 8(d) "reference-equivalent wall": the reference's OWN, unchanged coder.py (installed under oracle/_ref by build())
+    over the drop-in shims -- ASCII PLY read, ME.SparseTensor, Coder.encode (files + tmc3 subprocess), Coder.decode
+    (tmc3 + files) -- i.e. what `python coder.py` prints as Enc Time + Dec Time (coder.py:155-162), on this GPU."""
+    import tempfile
+    import torch
+    from oracle import refbin
+    if not refbin.reference_sources_installed():
+        return None
+    from pcgcv2_b200 import ops
+    coder = refbin.load_reference_coder()
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+        ply = os.path.join(tmp, "in.ply")
+        ops.ply_write_ascii(ply, pts)
+        os.makedirs(os.path.join(tmp, "output"))
+        model = coder.PCCModel().to(coder.device)
+        model.load_state_dict(refbin.reference_state_dict(sd))
+        c = coder.Coder(model=model, filename=os.path.join(tmp, "output", "in"))
+        out = {}
+        for rep in range(2):                                     # first pass warms the shim's weight packing
+            torch.cuda.synchronize()
+            t0 = time.time()
+            x = coder.load_sparse_tensor(ply, coder.device)
+            torch.cuda.synchronize()
+            t1 = time.time()
+            c.encode(x)
+            torch.cuda.synchronize()
+            t2 = time.time()
+            dec = c.decode(rho=1)
+            torch.cuda.synchronize()
+            t3 = time.time()
+            out = {"load_ply_ms": round(1e3 * (t1 - t0), 1), "encode_ms": round(1e3 * (t2 - t1), 1), "decode_ms": round(1e3 * (t3 - t2), 1),
+                   "encode_plus_decode_ms": round(1e3 * (t3 - t1), 1), "decoded_points": int(len(dec)),
+                   "bits": 8 * sum(os.path.getsize(os.path.join(tmp, "output", "in" + p)) for p in ("_C.bin", "_F.bin", "_H.bin", "_num_points.bin"))}
+        return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -124,6 +177,9 @@ def run_ours(args, rank, world, local_rank):
     from pcgcv2_b200 import dist as pdist
     from pcgcv2_b200.pipeline import FramePipeline
 
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    host_cores = pin_rank_threads(local_rank, local_world)
+    torch.set_num_threads(1)                                  # the frame threads are the parallelism; no intra-op pools per rank
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -136,10 +192,14 @@ def run_ours(args, rank, world, local_rank):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
-    pts = synth.synthetic_vox10(seed=rank, jitter=0.1 if world > 1 else 0.0)      # rank 0 @ N=1: 795 124 voxels
+    # config 3: every rank codes its own jittered cloud; --same-frames gives every rank rank 0's cloud (separates frame-size
+    # variance from host contention in the scaling numbers)
+    seed = 0 if args.same_frames else rank
+    pts = synth.synthetic_vox10(seed=seed, jitter=0.1 if (world > 1 and not args.same_frames) else 0.0)   # N=1: 795 124 voxels
     n0 = len(pts)
     depth = max(1, args.depth)
-    pipe = FramePipeline(load_weights("r3"), device=dev, depth=depth)             # `depth` frames in flight on this GPU
+    sd = load_weights("r3")
+    pipe = FramePipeline(sd, device=dev, depth=depth)          # `depth` frames in flight on this GPU
     codec = pipe.codecs[0]
     host_coords = torch.from_numpy(pts).pin_memory()
     dev_coords = host_coords.to(dev)
@@ -168,8 +228,8 @@ def run_ours(args, rank, world, local_rank):
             last = fn()
         end.record()
         barrier()
-        ms = pdist.max_over_ranks(start.elapsed_time(end), dev)
-        return ms, last, _lib.launch_count() - launches0, (t0, time.time())
+        own = start.elapsed_time(end)
+        return pdist.max_over_ranks(own, dev), last, _lib.launch_count() - launches0, (t0, time.time()), own
 
     for _ in range(args.warmup):
         st, out = step_device()
@@ -178,31 +238,38 @@ def run_ours(args, rank, world, local_rank):
         step_serial()
     assert out.shape[0] == n0, "decode did not return N0 voxels"
 
-    # roofline probe: the dominant kernel = k3 conv 16->16 on the finest decoder set (8*N1 rows)
-    probe_name = "decoder.conv2"
+    # roofline probes: (1) the dominant kernel = k3 conv 16->16 on the finest decoder set (8 N1 rows); (2) the widest layer,
+    # 64->64 on the 8 N3 candidate set, which runs on the tcgen05 / TMA kernel
+    probes = {"decoder.conv2": (16, 16), "decoder.conv0": (64, 64)}
     codec.record = {}
     step_serial()
-    _, probe_keys, _ = codec.record[probe_name]
+    sets = {"L0": "encoder.conv0", "L1": "encoder.conv1", "L2": "encoder.conv2", "L3": "encoder.conv3",
+            "U2": "decoder.conv0", "U1": "decoder.conv1", "U0": "decoder.conv2"}
+    rows, pairs = {}, {}
+    for tag, layer in sets.items():                           # rows and k=3 pairs of the seven coordinate sets (outside every timed region)
+        keys = codec.record[layer][1]
+        _, npairs = ops.kernel_map_k3(keys, ops.HashTable(keys), count_pairs=True)
+        rows[tag], pairs[tag] = int(keys.shape[0]), int(npairs.item())
     codec.record = None
-    _, npairs = ops.kernel_map_k3(probe_keys, ops.HashTable(probe_keys), count_pairs=True)
-    probe_n, probe_pairs = int(probe_keys.shape[0]), int(npairs.item())
-    del probe_keys
+    alg_convs, alg_all = pass_algorithmic_bytes(rows, pairs)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    codec.probe = {probe_name: []}                           # events on worker 0's stream, inside the timed region
-    ms_total, (st, out), launches, (t0, t1) = timed(step_device, args.steps)
-    probe_ms = [a.elapsed_time(b) for a, b in codec.probe[probe_name]]
+    codec.probe = {name: [] for name in probes}               # events on worker 0's stream, inside the timed region
+    ms_total, (st, out), launches, (t0, t1), ms_own = timed(step_device, args.steps)
+    probe_ms = {name: [a.elapsed_time(b) for a, b in ev] for name, ev in codec.probe.items()}
     codec.probe = {}
     clocks = sampler.stop(t0, t1) if sampler else None
-    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
-    codec.probe = {probe_name: []}                           # the same kernel with nothing else on the GPU
-    ms_serial, _, _, _ = timed(step_serial, args.steps)
-    probe_ms_serial = [a.elapsed_time(b) for a, b in codec.probe[probe_name]]
+    ms_e2e, _, _, _, ms_e2e_own = timed(step_e2e, args.steps)
+    codec.probe = {name: [] for name in probes}               # the same kernels with nothing else on the GPU
+    ms_serial, _, _, _, _ = timed(step_serial, args.steps)
+    probe_ms_serial = {name: [a.elapsed_time(b) for a, b in ev] for name, ev in codec.probe.items()}
     codec.probe = {}
     pipe.close()
 
     # the path's only collective: per-rank counters
-    counters = pdist.gather_counters(torch.tensor([n0 * depth, st.bits() * depth, out.shape[0]], dtype=torch.int64, device=dev))
+    mine = [n0 * depth, st.bits() * depth, out.shape[0], 8 * len(st.F) * depth, 8 * len(st.C or b"") * depth,
+            int(round(1e3 * ms_own / args.steps)), int(round(1e3 * ms_e2e_own / args.steps)), n0]
+    counters = pdist.gather_counters(torch.tensor(mine, dtype=torch.int64, device=dev))
     total_pts, total_bits = int(counters[:, 0].sum()), int(counters[:, 1].sum())
     if rank != 0:
         if world > 1:
@@ -211,46 +278,72 @@ def run_ours(args, rank, world, local_rank):
     ms_step = ms_total / args.steps
     value = pdist.aggregate_throughput(counters[:, 0], ms_step)
     e2e_value = pdist.aggregate_throughput(counters[:, 0], ms_e2e / args.steps)
-    # the dominant kernel's duration: CUDA events on its own stream in the serial timed region (nothing else on the GPU);
-    # inside the pipelined region the same events also span the time slices of the other frame's kernels
-    kern_ms, kern_ms_pipelined = float(np.mean(probe_ms_serial)), float(np.mean(probe_ms))
-    alg = k3_algorithmic_bytes(probe_n, probe_pairs, 16, 16)
-    achieved = alg / (kern_ms * 1e-3) / 1e9
+
+    def kernel_line(name, tag, cin, cout, what):
+        # duration: CUDA events on the kernel's own stream in the serial timed region (nothing else on the GPU); inside the
+        # pipelined region the same events also span the time slices of the other frame's kernels
+        ms, ms_pipe = float(np.mean(probe_ms_serial[name])), float(np.mean(probe_ms[name]))
+        alg = k3_algorithmic_bytes(rows[tag], pairs[tag], cin, cout)
+        ach = alg / (ms * 1e-3) / 1e9
+        return {"kernel": what, "rows": rows[tag], "pairs": pairs[tag], "algorithmic_bytes": alg, "kernel_ms": round(ms, 4),
+                "kernel_ms_in_pipelined_region": round(ms_pipe, 4), "achieved": round(ach, 1), "unit": "GB/s",
+                "frac": round(ach / hbm_peak, 4), "tflops": round(2 * pairs[tag] * cin * cout / (ms * 1e-3) / 1e12, 1)}
+
+    dom = kernel_line("decoder.conv2", "U0", 16, 16,
+                      "conv_k3_octet_h2_kernel<16,16> (decoder.conv2: k=3 conv 16->16 on the finest decoder set; pre-split f16 hi/lo "
+                      "features, mma.sync m16n8k16, 4x4x4 halo per octet staged in shared memory by cp.async)")
+    wide = kernel_line("decoder.conv0", "U2", 64, 64,
+                       "wide::conv_k3_wide_kernel<64,64> (decoder.conv0: k=3 conv 64->64 on the 8 N3 candidate set; tcgen05.mma kind::f16, "
+                       "accumulators in tensor memory, weight tiles by TMA bulk copy, h2 rows gathered into the SWIZZLE_128B operand)")
+    frame_ms = ms_step / depth
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32 (emulated on the tensor cores: operands f16 hi + f16 lo = 22 significand bits, f32 accumulation)",
+        "data": "synthetic",
         "config": {"workload": "synthetic_vox10(seed=rank) full 3-scale encode+decode, r3 weights, rho=1 "
-                               "(stand-in for longdress_vox10_1300.ply)",
+                               "(stand-in for longdress_vox10_1300.ply)" + (" [--same-frames: every rank codes seed 0]" if args.same_frames else ""),
                    "points_per_frame": n0, "frames_per_step": world * depth,
                    "parallelism": f"frames sharded over {world} GPU(s), {depth} frame(s) in flight per GPU (one host thread + "
                                   "CUDA stream each: the host range coder of one frame overlaps the kernels of the other)",
                    "serial_ms_per_frame": round(ms_serial / args.steps, 3), "host_cpus": len(os.sched_getaffinity(0)),
-                   "arithmetic": "k=3 / k=2 layers: operands split into f16 hi + f16 lo (22 significand bits), three tensor-core "
-                                 "products per term pair, f32 accumulation; remaining layers fp32 / 3xTF32",
-                   "bpp_features": round(total_bits / total_pts, 5),
-                   "coords_side_channel": "raw int32 hand-over (tmc3 subprocess out of scope)",
+                   "host_cores_per_rank": host_cores,
+                   "arithmetic": "k=3 / k=2 layers: operands split into f16 hi + f16 lo (22 significand bits), products on the tensor "
+                                 "cores (tcgen05.mma for 64->64, mma.sync elsewhere), f32 accumulation; remaining layers fp32 / 3xTF32",
+                   "bpp_total": round(total_bits / total_pts, 5),
+                   "bpp_features": round(int(counters[:, 3].sum()) / total_pts, 5),
+                   "bpp_coords": round(int(counters[:, 4].sum()) / total_pts, 5),
+                   "coords_side_channel": "in-process octree coder (own format, ~1.5 bits per bottleneck point; tmc3 gives ~1.0: parity runs "
+                                          "use Tmc3CoordinateCoder), coded and decoded inside every timed frame on a side thread",
+                   "cdf_table": "built on the host once per symbol range and cached: after warm-up no table work is left in the timed region",
+                   "per_rank": {"ms_per_step": [round(v / 1e3, 3) for v in counters[:, 5].tolist()],
+                                "e2e_ms_per_step": [round(v / 1e3, 3) for v in counters[:, 6].tolist()],
+                                "points_per_frame": counters[:, 7].tolist()},
                    "l2": "per-step traffic (~8.6 GB algorithmic, >1 GB live) exceeds the 126 MB L2; no flush needed"},
         # H2D: input voxels + (decode side) bottleneck coordinates and int16 symbols;
-        # D2H: decoded voxels + (encode side) bottleneck coordinates, int16 symbols and the uint16 table
+        # D2H: decoded voxels + (encode side) bottleneck coordinates and int16 symbols
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT,
                 "h2d_bytes_per_step": depth * int(host_coords.numel() * 4 + st.coords.size * 4 + st.coords.shape[0] * 8 * 2),
                 "d2h_bytes_per_step": depth * int(out.shape[0] * 3 * 4 + st.coords.size * 4 + st.coords.shape[0] * 8 * 2)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "conv_k3_octet_h2_kernel<16,16> (decoder.conv2: k=3 conv 16->16 on the "
-                                               "finest decoder set; pre-split f16 hi/lo features, mma.sync m16n8k16, "
-                                               "4x4x4 halo per octet staged in shared memory by cp.async)",
-                     "rows": probe_n, "pairs": probe_pairs, "algorithmic_bytes": alg,
-                     "kernel_ms": round(kern_ms, 4), "kernel_ms_in_pipelined_region": round(kern_ms_pipelined, 4),
+        "roofline": {"bound": "hbm", **dom, "peak": hbm_peak, "peak_source": peak_src,
                      "timed_in": f"{args.steps} one-frame-at-a-time steps inside bench.py (CUDA events on the launching stream); "
                                  "with 2 frames in flight the events also cover kernels of the other stream sharing the SMs",
-                     "achieved": round(achieved, 1), "peak": hbm_peak,
-                     "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
-                     "traffic": ncu_traffic_bytes()},
+                     "traffic": ncu_traffic_bytes(),
+                     "wide_layer": wide,
+                     "whole_pass": {"algorithmic_bytes_convs": alg_convs, "algorithmic_bytes_all": alg_all,
+                                    "frame_ms_pipelined": round(frame_ms, 3),
+                                    "frac": round(alg_convs / (frame_ms * 1e-3) / 1e9 / hbm_peak, 4),
+                                    "note": "106 convolutions' SURVEY 8(d) bytes / wall time per frame with 2 frames in flight (upper bound on "
+                                            "GPU-busy time) / HBM peak"}},
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(1)
+        try:
+            line["config"]["reference_equivalent_wall_ms"] = reference_equivalent_wall(pts, sd)
+        except Exception as e:                                 # the reference install is optional on the box
+            line["config"]["reference_equivalent_wall_ms"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        line["cpu_baseline"] = cpu_baseline(1, full_size=True)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -267,19 +360,28 @@ def cpu_pass(sd, pts):
     return time.time() - t, st
 
 
-def cpu_baseline(steps):
+def cpu_baseline(steps, full_size=False):
     """the oracle (a port of the reference's CPU algorithm: per-offset gather -> mm -> index_add) on the
-    box's host cores, on a bounded sample of the workload."""
+    box's host cores: one pass over the FULL 795 124-voxel cloud (the GPU arm's own workload) when ``full_size``, with the
+    half-scale sample the ``--impl reference`` arm steps over beside it."""
     import torch
     from pcgcv2_b200 import synth
     torch.set_flush_denormal(True)                          # 46 % of the r3 weights are denormals (SURVEY F6)
+    torch.set_num_threads(len(os.sched_getaffinity(0)))     # all host threads the oracle's torch ops can use
     sd = load_weights("r3")
     pts = synth.synthetic_vox10(seed=0, scale=CPU_SAMPLE_SCALE)
     secs = [cpu_pass(sd, pts)[0] for _ in range(steps)]
-    return {"value": round(len(pts) / float(np.mean(secs)) / 1e6, 5), "unit": UNIT, "cores": torch.get_num_threads(),
-            "kind": "port",
-            "sample": f"synthetic_vox10(seed=0, scale={CPU_SAMPLE_SCALE}): {len(pts)} voxels, full encode+decode, "
-                      f"{steps} pass(es), {np.mean(secs):.1f} s each, flush-denormal on"}
+    half = round(len(pts) / float(np.mean(secs)) / 1e6, 5)
+    out = {"value": half, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+           "sample": f"synthetic_vox10(seed=0, scale={CPU_SAMPLE_SCALE}): {len(pts)} voxels, full encode+decode, "
+                     f"{steps} pass(es), {np.mean(secs):.1f} s each, flush-denormal on"}
+    if full_size:
+        full = synth.synthetic_vox10(seed=0)
+        sec = cpu_pass(sd, full)[0]
+        out.update({"value": round(len(full) / sec / 1e6, 5), "half_scale_value": half,
+                    "sample": f"synthetic_vox10(seed=0): the full {len(full)}-voxel cloud of the GPU arm, one encode+decode pass, {sec:.1f} s, "
+                              f"flush-denormal on (half-scale sample of the --impl reference arm: {out['sample']})"})
+    return out
 
 
 def run_reference(args, rank, world):
@@ -288,6 +390,7 @@ def run_reference(args, rank, world):
     import torch
     from pcgcv2_b200 import synth
     torch.set_flush_denormal(True)
+    torch.set_num_threads(len(os.sched_getaffinity(0)))     # all host threads, whatever OMP_NUM_THREADS torchrun exported
     sd = load_weights("r3")
     pts = synth.synthetic_vox10(seed=0, scale=CPU_SAMPLE_SCALE)
     for _ in range(args.warmup):
@@ -318,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=2, help="frames in flight per GPU (1 = one frame at a time)")
+    ap.add_argument("--same-frames", action="store_true", help="every rank codes rank 0's cloud (no frame-size variance between ranks)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

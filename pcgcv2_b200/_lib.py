@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpcgc.so")
+LIB_PATH = os.environ.get("PCGC_LIB") or os.path.join(_HERE, "lib", "libpcgc.so")     # PCGC_LIB: a tuning-variant build (tools/)
 CSRC = os.path.join(_HERE, "csrc")
 
 

@@ -122,6 +122,10 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[W]) {
 #ifndef PCGC_WIDE_G
 #define PCGC_WIDE_G 10
 #endif
+#ifndef PCGC_WIDE_SMEM_KB
+#define PCGC_WIDE_SMEM_KB 224   // stage budget (measured: more stages in flight beat a bigger L1, profiles/r02_wide_tcgen05_*.txt)
+#endif
+
 
 template <int CIN, int COUT>
 struct WCfg {
@@ -143,13 +147,26 @@ struct WCfg {
     static_assert(NBUF * ACC_COLS <= 512, "accumulators exceed tensor memory");
     static constexpr int TMEM_COLS = NBUF * ACC_COLS <= 32 ? 32 : NBUF * ACC_COLS <= 64 ? 64 : NBUF * ACC_COLS <= 128 ? 128 :
                                      NBUF * ACC_COLS <= 256 ? 256 : 512;
-    static constexpr int BUDGET = 227 * 1024 - 1024 - 256;
-    static constexpr int S = BUDGET / STAGE_BYTES > 16 ? 16 : BUDGET / STAGE_BYTES;    // stages = offsets in flight per SM
-    static_assert(S >= 2, "wide conv: not enough shared memory for the pipeline");
+    static constexpr int BAR_BYTES = 512;                   // 2 S + 2 NBUF mbarriers + the TMEM base address
+    static constexpr int IDX_BYTES = CIN >= 32 ? 2 * 27 * TM * 4 : 0;                // lockstep mode: two kernel-map slices
+    static constexpr int BUDGET = 227 * 1024 - 1024 - BAR_BYTES - IDX_BYTES;
+    static constexpr int WANT = (PCGC_WIDE_SMEM_KB * 1024 < BUDGET ? PCGC_WIDE_SMEM_KB * 1024 : BUDGET) / STAGE_BYTES;
+    static constexpr int S = WANT > 16 ? 16 : (WANT < 2 ? 2 : WANT);                   // stages = offsets in flight per SM
+    static_assert(S * STAGE_BYTES <= BUDGET, "wide conv: stages exceed shared memory");
+    // Gather organisation (measured, profiles/r02_wide_tcgen05_*.txt):
+    //  * LOCKSTEP (cin >= 32: few, big stages): all gather warps share the rows of every offset and each keeps D older
+    //    offsets in flight (cp.async groups); the tile's kernel-map slice is staged in shared memory;
+    //  * otherwise (cin <= 16: many small stages): ONE warp per offset, min(GATHER_WARPS, S) offsets in flight per SM -- a
+    //    warp's wait-stage / issue / wait-data / proxy-fence / arrive round trip overlaps with the other warps' offsets.
+    static constexpr bool LOCKSTEP = CIN >= 32;
+    static constexpr int D = S - 1 > 4 ? 4 : S - 1;
+    static constexpr int TEAM = LOCKSTEP ? GATHER_WARPS : 1;                          // arrivals per stage from the gather side
+    static constexpr int NT = GATHER_WARPS < S ? GATHER_WARPS : S;                    // per-warp mode: active warps (<= S: parity waits)
     static constexpr int EPI_WARPS = 4, MMA_WARP = 4, PROD_WARP = 5, FIRST_GATHER = 6;
     static constexpr int THREADS = 32 * (FIRST_GATHER + GATHER_WARPS);
-    static constexpr size_t OFF_STAGE = 0, OFF_BAR = (size_t)S * STAGE_BYTES;
-    static constexpr size_t SMEM = OFF_BAR + 256 + 1024;    // + slack for the 1024-byte alignment SWIZZLE_128B needs
+    static constexpr size_t OFF_STAGE = 0, OFF_IDX = (size_t)S * STAGE_BYTES, OFF_BAR = OFF_IDX + IDX_BYTES;
+    static constexpr size_t SMEM = OFF_BAR + BAR_BYTES + 1024;   // + slack for the 1024-byte alignment SWIZZLE_128B needs
+    static_assert((2 * S + 2 * NBUF) * 8 + 8 <= BAR_BYTES, "barrier region too small");
     static constexpr size_t packed_bytes() { return (size_t)27 * B_BYTES; }
     __host__ __device__ static constexpr int group_of(int k) { return k * NG / 27; }
 };
@@ -199,7 +216,7 @@ conv_k3_wide_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *_
 
     // ---- one-time setup: barriers, tensor memory
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(full + s, 2); mbar_init(empty + s, 1); }   // full: gather warp + weight producer
+        for (int s = 0; s < S; ++s) { mbar_init(full + s, C::TEAM + 1); mbar_init(empty + s, 1); }   // full: the gather team + the weight producer
         for (int b = 0; b < NBUF; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, C::EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -215,50 +232,101 @@ conv_k3_wide_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *_
 
     if (warp >= C::FIRST_GATHER) {
         // =========================== GATHER warps ===========================
-        // Warp gw owns the offsets g = gw, gw + G, gw + 2 G, ... of this CTA's sequence (g = 27 * tile iteration + k) and
-        // copies ALL 128 rows of an offset: a warp's round trip (wait for the stage, issue, wait for the data, proxy fence,
-        // arrive: ~700 cycles of latency) overlaps with the other warps' offsets instead of being paid once per offset by
-        // all of them in lockstep (measured: 650 cycles per offset whatever the pipeline depth when the rows of one offset
-        // were spread over the warps).
-        const int gw = warp - C::FIRST_GATHER;
-        constexpr int G = C::GATHER_WARPS;
         constexpr int RPI = 32 / CPR;                            // rows per warp instruction (4 x 128 / 8 x 64 / 16 x 32 bytes)
-        const int sub = lane / CPR, c = lane % CPR;
-        const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const int64_t total = my_tiles * 27;
-        auto load_idx = [&](int64_t g, int32_t (&idx)[4]) {      // kernel-map entries of rows lane, lane + 32, ... of offset g
-            const int64_t tile = blockIdx.x + (g / 27) * gridDim.x;
-            const int k = (int)(g % 27);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int64_t grow = tile * TM + 32 * j + lane;
-                idx[j] = (g < total && grow < n) ? __ldg(nbr + (int64_t)k * n + grow) : -1;
-            }
-        };
-        int32_t idx_cur[4], idx_nxt[4];
-        load_idx(gw, idx_cur);
-        for (int64_t g = gw; g < total; g += G) {
-            load_idx(g + G, idx_nxt);                            // in flight during this offset's copies
-            const uint32_t slot = (uint32_t)(g % S), ph = (uint32_t)((g / S) & 1);
-            if (lane == 0) mbar_wait(empty + slot, ph ^ 1);      // the MMAs that read this stage have retired
-            __syncwarp();
-            const uint32_t a_s = smem_u32(sm + C::OFF_STAGE + (size_t)slot * C::STAGE_BYTES);
-#pragma unroll
-            for (int q = 0; q < TM / RPI; ++q) {                 // RPI rows x one K block per instruction
-                const int row = RPI * q + sub;
-                const int32_t src_row = __shfl_sync(0xffffffffu, idx_cur[(RPI * q) / 32], (RPI * q) % 32 + sub);
-                const uint32_t *src = in + (int64_t)(src_row < 0 ? 0 : src_row) * in_ld + 4 * c;
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb)
-                    cp_async16_zfill(a_s + sw_off<TM, RB>(row, kb, c), src + 4 * CPR * kb, src_row >= 0);
-            }
+        const int gw = warp - C::FIRST_GATHER, sub = lane / CPR, c = lane % CPR;
+        const uint32_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+        if constexpr (C::LOCKSTEP) {
+            constexpr int GT = 32 * C::GATHER_WARPS, D = C::D;
+            constexpr int INSTR = TM / RPI * KB;                 // warp instructions per offset, dealt round the warps
+            int32_t *idx_s = reinterpret_cast<int32_t *>(sm + C::OFF_IDX);
+            const int gt = threadIdx.x - 32 * C::FIRST_GATHER;
+            auto stage_idx = [&](int64_t tile, int32_t *dst) {   // kernel-map slice of a tile -> shared memory (async)
+                for (int i = gt; i < 27 * TM; i += GT) {
+                    const int k = i / TM, r = i % TM;
+                    const int64_t grow = tile * TM + r;
+                    const bool ok = grow < n;                    // rows past the end read as index 0: gathered, never stored
+                    cp_async4_zfill(smem_u32(dst + i), nbr + (ok ? (int64_t)k * n + grow : 0), ok);
+                }
+            };
+            if (my_tiles) stage_idx(blockIdx.x, idx_s);
             cp_async_commit();
-            cp_async_wait<0>();                                  // this warp's copies of the offset have landed
-            fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full + slot);
+            cp_async_wait<0>();
+            asm volatile("bar.sync 1, %0;" ::"n"(GT) : "memory");
+            uint32_t g = 0;                                      // offsets issued so far (stage = g % S)
+            for (uint32_t titer = 0; titer < my_tiles; ++titer) {
+                const int64_t tile = blockIdx.x + (int64_t)titer * gridDim.x;
+                const int32_t *idx_t = idx_s + (titer & 1) * 27 * TM;
+                if (titer + 1 < my_tiles) stage_idx(tile + gridDim.x, idx_s + ((titer + 1) & 1) * 27 * TM);   // joins the first group below
+                for (int it = 0; it < 27 + D; ++it) {
+                    if (it < 27) {
+                        const uint32_t gi = g + it, slot = gi % S, ph = (gi / S) & 1;
+                        if (lane == 0) mbar_wait(empty + slot, ph ^ 1);      // the MMAs that read this stage have retired
+                        __syncwarp();
+                        const uint32_t a_s = smem_u32(sm + C::OFF_STAGE + (size_t)slot * C::STAGE_BYTES);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) idx_cur[j] = idx_nxt[j];
+                        for (int i = 0; i < (INSTR + C::GATHER_WARPS - 1) / C::GATHER_WARPS; ++i) {
+                            const int q = gw + C::GATHER_WARPS * i;
+                            if (q < INSTR) {
+                                const int row = RPI * (q / KB) + sub, kb = q % KB;
+                                const int32_t src_row = idx_t[it * TM + row];
+                                const uint32_t *src = in + (int64_t)(src_row < 0 ? 0 : src_row) * in_ld + 4 * (CPR * kb + c);
+                                cp_async16_zfill(a_s + sw_off<TM, RB>(row, kb, c), src, src_row >= 0);
+                            }
+                        }
+                    }
+                    cp_async_commit();
+                    if (it >= D) {
+                        cp_async_wait<D>();                                  // this thread's copies of offset it - D have landed
+                        fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full + (g + it - D) % S);
+                    }
+                }
+                g += 27;
+                asm volatile("bar.sync 1, %0;" ::"n"(GT) : "memory");        // next tile's kernel-map slice is complete for all
+            }
+            cp_async_wait<0>();
+        } else {
+            // one warp per offset: warp gw owns g = gw, gw + NT, ... (g = 27 * tile iteration + k) and copies all 128 rows.
+            // Only NT = min(GATHER_WARPS, S) warps take part: a warp waits for its stage by PHASE PARITY, which is sound only
+            // while no waiter is more than one phase ahead of the barrier -- with NT <= S the stage of g + NT was last used by
+            // g + NT - S <= g, which this warp has itself seen retire.
+            constexpr uint32_t NT = C::NT;
+            const uint32_t total = my_tiles * 27u;
+            auto load_idx = [&](uint32_t g, int32_t (&idx)[4]) { // kernel-map entries of rows lane, lane + 32, ... of offset g
+                const int64_t tile = blockIdx.x + (int64_t)(g / 27u) * gridDim.x;
+                const uint32_t k = g % 27u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t grow = tile * TM + 32 * j + lane;
+                    idx[j] = (g < total && grow < n) ? __ldg(nbr + (int64_t)k * n + grow) : -1;
+                }
+            };
+            int32_t idx_cur[4], idx_nxt[4];
+            load_idx((uint32_t)gw, idx_cur);
+            for (uint32_t g = (uint32_t)gw; (uint32_t)gw < NT && g < total; g += NT) {
+                load_idx(g + NT, idx_nxt);                       // in flight during this offset's copies
+                const uint32_t slot = g % S, ph = (g / S) & 1;
+                if (lane == 0) mbar_wait(empty + slot, ph ^ 1);  // the MMAs that read this stage have retired
+                __syncwarp();
+                const uint32_t a_s = smem_u32(sm + C::OFF_STAGE + (size_t)slot * C::STAGE_BYTES);
+#pragma unroll
+                for (int q = 0; q < TM / RPI; ++q) {             // RPI rows x one K block per instruction
+                    const int row = RPI * q + sub;
+                    const int32_t src_row = __shfl_sync(0xffffffffu, idx_cur[(RPI * q) / 32], (RPI * q) % 32 + sub);
+                    const uint32_t *src = in + (int64_t)(src_row < 0 ? 0 : src_row) * in_ld + 4 * c;
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+                        cp_async16_zfill(a_s + sw_off<TM, RB>(row, kb, c), src + 4 * CPR * kb, src_row >= 0);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();                              // this warp's copies of the offset have landed
+                fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full + slot);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) idx_cur[j] = idx_nxt[j];
+            }
         }
     } else if (warp == C::PROD_WARP) {
         // =========================== weight PRODUCER (TMA bulk copies) ===========================
