@@ -59,6 +59,17 @@ uint64_t pcgc_launch_count(void);
 int pcgc_pack_keys(const int32_t *coords, int64_t n, int32_t tensor_stride, uint64_t *keys,
                    int32_t *err_flag, void *stream);
 
+/* the same from int32 [n,3] = (x,y,z) rows with one batch index for all rows (coder.py is
+ * batch-1 by construction, coder.py:97,106): no padded [n,4] copy of the cloud is needed. */
+int pcgc_pack_keys3(const int32_t *coords3, int64_t n, int32_t tensor_stride, int32_t batch, uint64_t *keys,
+                    int32_t *err_flag, void *stream);
+
+/* a5  gather map of ME.MinkowskiConvolution(k=2, s=2) -- autoencoder.py:78,97,116: child_map
+ * int32 [8][n_parents], entry [k][p] = row of child k (= key & 7 = ix + 2 iy + 4 iz) of parent p
+ * or -1; parent_of int32 [n] comes from pcgc_stride_down. */
+int pcgc_child_map_k2(const uint64_t *child_keys, const int32_t *parent_of, int64_t n, int64_t n_parents,
+                      int32_t *child_map, void *stream);
+
 /* scale_sparse_tensor(x, factor) -- data_utils.py:112-118 (coder.py:149-152,166-167): every
  * coordinate value v -> (int) round_half_even((float) v * factor); `count` = number of int32
  * values (rows x columns; pass the spatial columns only).  The duplicate rows the down-scaling

@@ -176,6 +176,7 @@ class Codec:
         self._h2_on = bool(self.packed_h2)
         self.use_octet = use_octet_kernels
         self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)   # raised by an h2 producer: re-run in fp32
+        self._bad = torch.zeros(1, dtype=torch.int32, device=self.device)        # raised by pack_keys: coordinate out of range
         self.h2_fallbacks = 0
         self.fuse_irn = fuse_irn        # InceptionResNet blocks through pcgc_irn_fwd (one C call per block)
         self._irn_plans = {}
@@ -383,7 +384,7 @@ class Codec:
         """int32 [N,4] on the device -> (level-0 coordinate set in Morton order, device flag "has duplicates").
         Duplicates are rare: the first pass only raises the flag (read together with the symbol range, no extra
         synchronisation); ``dedupe`` drops them (``unique_consecutive`` synchronises for the output size)."""
-        keys = ops.pack_keys(coords, 1)
+        keys = ops.pack_keys_async(coords, 1, self._bad)             # range flag: read with the pass's synchronising read
         keys, _ = ops.argsort_u64(keys)
         if dedupe:
             keys = torch.unique_consecutive(keys)
@@ -536,8 +537,8 @@ class Codec:
 
     def _encode_pass(self, coords, dedupe=False):
         coords = torch.as_tensor(coords, dtype=torch.int32).to(self.device, non_blocking=True)   # async from pinned host memory
-        if coords.shape[1] == 3:                                          # batch column added on the device
-            coords = torch.nn.functional.pad(coords, (1, 0))
+        if coords.dim() != 2 or coords.shape[1] not in (3, 4):
+            raise ValueError("coordinates must be int32 [N,3] (x,y,z) or [N,4] (batch,x,y,z)")
         self._dedupe_next = dedupe
         level0, dup = self._sorted_input(coords, dedupe)
         y, level3, num_points = self.analysis(level0)
@@ -546,13 +547,17 @@ class Codec:
         y, c3 = y[order].contiguous(), c3[order].contiguous()
         sym, mm = ops.eb_quantize_async(y)
         # one synchronising read for everything the host needs: symbol range + flags, symbols, coordinates
-        flags_h = self._staging("flags", (4,), torch.int32)
+        flags_h = self._staging("flags", (5,), torch.int32)
         sym_h, c3_h = self._staging("sym", tuple(sym.shape), torch.int16), self._staging("c3", tuple(c3.shape), torch.int32)
-        flags_h.copy_(torch.cat([mm, self._overflow, dup]), non_blocking=True)
+        flags_h.copy_(torch.cat([mm, self._overflow, dup, self._bad]), non_blocking=True)
         sym_h.copy_(sym, non_blocking=True)
         c3_h.copy_(c3, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        lo, hi, over, has_dup = flags_h.tolist()
+        lo, hi, over, has_dup, bad = flags_h.tolist()
+        if bad:
+            self._bad.zero_()
+            self._overflow.zero_()
+            raise ValueError("coordinates out of range: need 0 <= c <= %d, batch <= 126" % ((1 << 19) - 1))
         if has_dup:
             if over:
                 self._overflow.zero_()                                    # the deduplicated re-run decides for itself
@@ -591,7 +596,7 @@ class Codec:
         c3_h.copy_(torch.as_tensor(coords_in, dtype=torch.int32))
         c3 = c3_h.to(self.device, non_blocking=True)
         c3 = c3[self._canonical_order(c3)]                               # coder.py:97-99 (runs while the host decodes the symbols)
-        keys = ops.pack_keys(torch.nn.functional.pad(c3 * 8, (1, 0)), 8)
+        keys = ops.pack_keys_async(c3, 1, self._bad)                      # = the stride-8 keys of 8 * c3 (keys hold coordinate / stride)
         if stream.C is None:
             ops.rc_decode_u16(self._host_table(lo, hi), stream.F, n3 * ch, out=sym_h.numpy().reshape(-1))
         y = sym_h.to(self.device, non_blocking=True).float() + float(lo)
@@ -601,14 +606,25 @@ class Codec:
         nums[-1] = int(rho * nums[-1])                                   # coder.py:107
         level0, _, _ = self.synthesis(y[order.long()].contiguous(), level3, nums)
         out = ops.unpack_keys(level0.keys, 1)[:, 1:]
+        flag_h = self._staging("flag_out", (2,), torch.int32)
+        flag_h.copy_(torch.cat([self._overflow, self._bad]), non_blocking=True)
         if not to_host:
-            return None if self._h2_overflowed() else out
-        out = out.contiguous()
-        host = self._staging("out", tuple(out.shape), torch.int32)       # D2H through a reusable pinned buffer
-        flag_h = self._staging("flag_out", (1,), torch.int32)
-        host.copy_(out, non_blocking=True)
-        flag_h.copy_(self._overflow, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            torch.cuda.current_stream().synchronize()
+        else:
+            out = out.contiguous()
+            host = self._staging("out", tuple(out.shape), torch.int32)   # D2H through a reusable pinned buffer
+            host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        if int(flag_h[1]):
+            self._bad.zero_()
+            self._overflow.zero_()
+            raise ValueError("bottleneck coordinates out of range")
+        if not to_host:
+            if self._h2_on and int(flag_h[0]):
+                self._overflow.zero_()
+                self.h2_fallbacks += 1
+                return None
+            return out
         if self._h2_on and int(flag_h[0]):
             self._overflow.zero_()
             self.h2_fallbacks += 1

@@ -24,6 +24,30 @@ __global__ void pack_keys_kernel(const int4 *__restrict__ coords, int64_t n, int
     }
 }
 
+// the same from int32 [n,3] (x, y, z) rows with one batch index for all (Codec's input: no padded copy of the cloud)
+__global__ void pack_keys3_kernel(const int32_t *__restrict__ coords, int64_t n, int32_t stride, int32_t batch,
+                                  uint64_t *__restrict__ keys, int32_t *__restrict__ err) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cx = coords[3 * i], cy = coords[3 * i + 1], cz = coords[3 * i + 2];
+        const int x = cx / stride, y = cy / stride, z = cz / stride;
+        const bool bad = (cx < 0) | (cy < 0) | (cz < 0) | (x > PCGC_MAX_COORD) | (y > PCGC_MAX_COORD) | (z > PCGC_MAX_COORD) |
+                         (x * stride != cx) | (y * stride != cy) | (z * stride != cz);
+        if (bad) {
+            *err = 1;
+            keys[i] = 0;
+        } else {
+            keys[i] = make_key((uint32_t)batch, (uint32_t)x, (uint32_t)y, (uint32_t)z);
+        }
+    }
+}
+
+// child_map[k][p] = row of child k (= key & 7) of parent p, -1 where absent (the gather map of the k=2 stride-2 convolution)
+__global__ void child_map_k2_kernel(const uint64_t *__restrict__ child_keys, const int32_t *__restrict__ parent_of, int64_t n,
+                                    int64_t n_parents, int32_t *__restrict__ child_map) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        child_map[(int64_t)(child_keys[i] & 7) * n_parents + parent_of[i]] = (int32_t)i;
+}
+
 __global__ void unpack_keys_kernel(const uint64_t *__restrict__ keys, int64_t n, int32_t stride,
                                    int4 *__restrict__ coords) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -226,6 +250,24 @@ int pcgc_pack_keys(const int32_t *coords, int64_t n, int32_t tensor_stride, uint
     pack_keys_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>((const int4 *)coords, n, tensor_stride,
                                                                            keys, err_flag);
     return check_launch("pack_keys");
+}
+
+int pcgc_pack_keys3(const int32_t *coords3, int64_t n, int32_t tensor_stride, int32_t batch, uint64_t *keys, int32_t *err_flag,
+                    void *stream) {
+    PCGC_REQUIRE(n >= 0 && tensor_stride >= 1 && batch >= 0 && batch <= PCGC_MAX_BATCH, "pcgc_pack_keys3: bad arguments");
+    if (n == 0) return PCGC_OK;
+    pack_keys3_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(coords3, n, tensor_stride, batch, keys, err_flag);
+    return check_launch("pack_keys3");
+}
+
+int pcgc_child_map_k2(const uint64_t *child_keys, const int32_t *parent_of, int64_t n, int64_t n_parents, int32_t *child_map,
+                      void *stream) {
+    PCGC_REQUIRE(n >= 0 && n_parents >= 0, "pcgc_child_map_k2: bad sizes");
+    if (n_parents == 0) return PCGC_OK;
+    PCGC_CUDA(cudaMemsetAsync(child_map, 0xFF, sizeof(int32_t) * 8 * (size_t)n_parents, (cudaStream_t)stream));   // -1 everywhere
+    if (n == 0) return PCGC_OK;
+    child_map_k2_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(child_keys, parent_of, n, n_parents, child_map);
+    return check_launch("child_map_k2");
 }
 
 int pcgc_unpack_keys(const uint64_t *keys, int64_t n, int32_t tensor_stride, int32_t *coords, void *stream) {

@@ -72,6 +72,23 @@ def pack_keys(coords: torch.Tensor, tensor_stride: int) -> torch.Tensor:
     return keys
 
 
+def pack_keys_async(coords: torch.Tensor, tensor_stride: int, err: torch.Tensor, batch: int = 0) -> torch.Tensor:
+    """int32 [N,4] (b,x,y,z) or [N,3] (x,y,z; all rows in ``batch``) -> int64 [N] Morton keys WITHOUT reading the range flag
+    back: ``err`` (device int32 [1], zeroed by the caller) is raised on a bad coordinate; the caller reads it with its next
+    synchronising read."""
+    _need_cuda(coords)
+    if coords.dtype != torch.int32:
+        raise ValueError("coordinates must be int32")
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    keys = torch.empty(n, dtype=torch.int64, device=coords.device)
+    if coords.shape[1] == 3:
+        check(_lib.lib().pcgc_pack_keys3(_p(coords), n, int(tensor_stride), int(batch), _p(keys), _p(err), _stream()), "pcgc_pack_keys3")
+    else:
+        check(_lib.lib().pcgc_pack_keys(_p(coords), n, int(tensor_stride), _p(keys), _p(err), _stream()), "pcgc_pack_keys")
+    return keys
+
+
 def scale_coords(coords: torch.Tensor, factor: float) -> torch.Tensor:
     """int32 coordinate values -> round_half_even(float32(v) * float32(factor)) (scale_sparse_tensor, data_utils.py:112-118);
     duplicates are NOT removed here."""
@@ -439,9 +456,9 @@ class PackedDownH2:
 
 def child_map_k2(child_keys, parent_of, n_parents):
     """int32 [8, n_parents]: row of child k = key & 7 of every parent, -1 where the child is absent."""
-    n = child_keys.shape[0]
-    cm = torch.full((8, n_parents), -1, dtype=torch.int32, device=child_keys.device)
-    cm[(child_keys & 7), parent_of.long()] = torch.arange(n, dtype=torch.int32, device=child_keys.device)
+    cm = torch.empty((8, n_parents), dtype=torch.int32, device=child_keys.device)
+    check(_lib.lib().pcgc_child_map_k2(_p(child_keys), _p(parent_of), child_keys.shape[0], int(n_parents), _p(cm), _stream()),
+          "pcgc_child_map_k2")
     return cm
 
 
