@@ -392,6 +392,19 @@ int pcgc_d1_sqdist(const uint64_t *query_keys, int64_t n_query, const uint64_t *
                    const uint64_t *cloud_keys, int64_t n_cloud, int32_t max_radius, uint64_t *acc3, int32_t *open_list,
                    void *stream);
 
+/* ---- k=3 convolution on FULL-OCTET sets on the 5th-generation tensor cores (row a3; csrc/conv_octet_tc05.cuh) ----
+ * Same layer and contract as pcgc_conv_k3_octet_h2_fwd (h2 features of the 8-child expansion in, the PARENT set's
+ * kernel map, fp32 and/or h2 rows out, fused bias / residual / ReLU, overflow flag) for cin = 16, cout in
+ * {1,4,8,16}: the 4x4x4 halos of 32 octets are staged once per tile and the 27 kernel offsets are 27 descriptor
+ * start addresses of tcgen05.mma (M = 64) into that halo; weights resident (TMA bulk copy), accumulators in TMEM.
+ * `packed` from pcgc_conv_k3_octet_tc05_pack_weights (.._packed_bytes bytes; 0 = no kernel for the shape). */
+size_t pcgc_conv_k3_octet_tc05_packed_bytes(int32_t cin, int32_t cout);
+int pcgc_conv_k3_octet_tc05_pack_weights(const float *weight, int32_t cin, int32_t cout, float scale, void *packed, void *stream);
+int pcgc_conv_k3_octet_tc05_fwd(const uint32_t *feats_h2, int32_t in_ld, const int32_t *parent_nbr, int64_t n_parents,
+                                const void *packed, float inv_scale, const float *bias, int32_t cin, int32_t cout,
+                                const float *residual, int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2,
+                                int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream);
+
 /* ---- ASCII PLY geometry I/O (row f2; HOST functions, synchronous) ---------------------------
  * read_ply_ascii_geo / write_ply_ascii_geo -- data_utils.py:19-48 (coder.py:26,33,128,177).
  * The reader keeps the reference's line semantics: a line is split at single spaces; if any

@@ -70,6 +70,10 @@ SIGNATURES = {
     "pcgc_conv_k3_wide_pack_weights": (ctypes.c_int, [c_p, c_i32, c_i32, ctypes.c_float, c_p, c_p]),
     "pcgc_conv_k3_wide_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, ctypes.c_float, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32,
                                               c_p, c_i32, c_i32, c_p, c_p]),
+    "pcgc_conv_k3_octet_tc05_packed_bytes": (c_sz, [c_i32, c_i32]),
+    "pcgc_conv_k3_octet_tc05_pack_weights": (ctypes.c_int, [c_p, c_i32, c_i32, ctypes.c_float, c_p, c_p]),
+    "pcgc_conv_k3_octet_tc05_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, ctypes.c_float, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32,
+                                                    c_p, c_i32, c_i32, c_p, c_p]),
     "pcgc_conv_k3_octet_h2_supported": (ctypes.c_int, [c_i32, c_i32]),
     "pcgc_conv_k3_octet_h2_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, ctypes.c_float, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32,
                                                   c_p, c_i32, c_i32, c_p, c_p]),

@@ -429,6 +429,47 @@ def conv_k3_wide(feats_h2, nbr, pw: PackedK3Wide, bias=None, residual=None, relu
     return out, out_h2
 
 
+class PackedK3OctetTc05:
+    """k=3 weights as the resident tcgen05 operand tiles of csrc/conv_octet_tc05.cuh (None: no kernel for the shape)."""
+
+    @staticmethod
+    def supported(cin, cout) -> bool:
+        return int(_lib.lib().pcgc_conv_k3_octet_tc05_packed_bytes(int(cin), int(cout))) > 0
+
+    def __init__(self, weight: torch.Tensor):
+        assert weight.dim() == 3 and weight.shape[0] == 27 and weight.is_contiguous()
+        self.cin, self.cout = int(weight.shape[1]), int(weight.shape[2])
+        n = int(_lib.lib().pcgc_conv_k3_octet_tc05_packed_bytes(self.cin, self.cout))
+        self.packed = None
+        if n:
+            self.scale, self.inv_scale = _h2_scale(weight)
+            self.packed = torch.empty(n, dtype=torch.uint8, device=weight.device)
+            check(_lib.lib().pcgc_conv_k3_octet_tc05_pack_weights(_p(weight), self.cin, self.cout, self.scale, _p(self.packed), _stream()),
+                  "pcgc_conv_k3_octet_tc05_pack_weights")
+
+
+def conv_k3_octet_tc05(feats_h2, parent_nbr, pw: PackedK3OctetTc05, bias=None, residual=None, relu=False, out=None, out_h2=None,
+                       want_f32=True, want_h2=False, overflow=None):
+    """k=3 convolution over h2 features on the 8-child expansion of a parent set, tcgen05 with descriptor-addressed halos."""
+    x = _h2(feats_h2)
+    n, cin = x.shape
+    n_par = parent_nbr.shape[1]
+    assert cin == pw.cin and pw.packed is not None and n == 8 * n_par and parent_nbr.is_contiguous()
+    if want_f32 or out is not None:
+        out = _out_slice(out, n, pw.cout, x.device)
+    if want_h2 and out_h2 is None:
+        out_h2 = torch.empty((n, pw.cout), dtype=torch.int32, device=x.device)
+    if out_h2 is not None:
+        assert out_h2.shape[0] == n and out_h2.shape[1] == pw.cout and out_h2.dtype == torch.int32 and out_h2.stride(1) == 1
+    residual = None if residual is None else _feat(residual)
+    check(_lib.lib().pcgc_conv_k3_octet_tc05_fwd(_p(x), x.stride(0), _p(parent_nbr), n_par, _p(pw.packed), pw.inv_scale, _p(bias), cin,
+                                                 pw.cout, _p(residual), 0 if residual is None else residual.stride(0), _p(out),
+                                                 0 if out is None else out.stride(0), _p(out_h2),
+                                                 0 if out_h2 is None else out_h2.stride(0), EPI_RELU if relu else 0, _p(overflow),
+                                                 _stream()), "pcgc_conv_k3_octet_tc05_fwd")
+    return out, out_h2
+
+
 _SUPPORT = {}
 
 

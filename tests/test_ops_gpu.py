@@ -467,6 +467,51 @@ def test_conv_k3_octet_h2_vs_oracle(cin, cout):
         assert _rel_err(got, torch.relu(S.conv_k3(f[:8 * n_par], cc, 1, w, b))) < H2_TOL
 
 
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 8), (16, 4), (16, 1)])
+def test_conv_k3_octet_tcgen05_vs_oracle(cin, cout):
+    """full-octet tcgen05 kernel (27 kernel offsets = 27 descriptor start addresses into one staged halo, M = 64 accumulators
+    interleaved in tensor memory) == oracle on the 8-child expansion, both outputs, fused epilogue, slices, tile tails."""
+    par = _surface()[:6007]
+    par[:, 1:] *= 2
+    pkeys, _ = ops.argsort_u64(_keys(par, 2))
+    pnbr = ops.kernel_map_k3(pkeys, ops.HashTable(pkeys))
+    c = ops.unpack_keys(ops.upsample_keys(pkeys), 1).cpu().numpy()
+    g = torch.Generator().manual_seed(cin * 17 + cout)
+    f = torch.randn(len(c), cin, generator=g) * 3.0
+    w = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    b = torch.randn(1, cout, generator=g)
+    ref = S.conv_k3(f, c, 1, w, b)
+    assert ops.PackedK3OctetTc05.supported(cin, cout)
+    pw = ops.PackedK3OctetTc05(w.to(DEV))
+    xh = ops.split_h2(f.to(DEV))
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    got, got_h = ops.conv_k3_octet_tc05(xh, pnbr, pw, b.to(DEV), want_h2=cout % 4 == 0, overflow=flag)
+    err = _rel_err(got, ref)
+    print(f"octet tcgen05 {cin}->{cout}: rel err {err:.2e}")
+    assert err < H2_TOL
+    if cout % 4 == 0:
+        assert _rel_err(ops.join_h2(got_h), ref) < H2_TOL
+        res = torch.randn(len(c), cout, generator=g)
+        wide = torch.full((len(c), cout + 8), -7.0, device=DEV)
+        wide_h = torch.full((len(c), cout + 8), 5, dtype=torch.int32, device=DEV)
+        ops.conv_k3_octet_tc05(xh, pnbr, pw, b.to(DEV), residual=res.to(DEV), relu=True, out=wide[:, 4:4 + cout], out_h2=wide_h[:, 4:4 + cout])
+        want = torch.relu(ref + res)
+        assert _rel_err(wide[:, 4:4 + cout], want) < H2_TOL and _rel_err(ops.join_h2(wide_h[:, 4:4 + cout]), want) < H2_TOL
+        assert (wide[:, :4] == -7).all() and (wide[:, 4 + cout:] == -7).all()
+        assert (wide_h[:, :4] == 5).all() and (wide_h[:, 4 + cout:] == 5).all()
+        wide_in = torch.zeros((len(c), cin + 4), dtype=torch.int32, device=DEV)
+        wide_in[:, 4:] = xh
+        assert _rel_err(ops.conv_k3_octet_tc05(wide_in[:, 4:], pnbr, pw, b.to(DEV))[0], ref) < H2_TOL
+    assert int(flag.item()) == 0
+    assert torch.equal(ops.conv_k3_octet_tc05(xh, pnbr, pw, b.to(DEV))[0], got)       # deterministic
+    for n_par in (1, 3, 31, 33, 257):                             # tile tails, fewer tiles than SMs
+        pk = pkeys[:n_par].contiguous()
+        nb = ops.kernel_map_k3(pk, ops.HashTable(pk))
+        cc = ops.unpack_keys(ops.upsample_keys(pk), 1).cpu().numpy()
+        got = ops.conv_k3_octet_tc05(ops.split_h2(f[:8 * n_par].to(DEV)), nb, pw, b.to(DEV), relu=True)[0]
+        assert _rel_err(got, torch.relu(S.conv_k3(f[:8 * n_par], cc, 1, w, b))) < H2_TOL
+
+
 def test_rowlane_layers_write_h2_copy_in_epilogue():
     """k=1 / k=2 s=2 / transposed k=2 s=2 with the fused h2 output: fp32 result unchanged, h2 copy == split of it."""
     g = torch.Generator().manual_seed(9)

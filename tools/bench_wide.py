@@ -39,7 +39,9 @@ def timeit(fn, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--only", default="", help='e.g. "8N3 110k:64x64" -- one set and shape, tcgen05 kernel only (for ncu captures)')
     args = ap.parse_args()
+    only_set, only_shape = (args.only.split(":") + [""])[:2] if args.only else ("", "")
     dev = torch.device("cuda")
     pts = synth.synthetic_vox10(0)
     keys0, _ = ops.argsort_u64(ops.pack_keys(torch.nn.functional.pad(torch.from_numpy(pts).to(dev), (1, 0)), 1))
@@ -54,12 +56,16 @@ def main():
     g = torch.Generator().manual_seed(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for name, shapes in SHAPES.items():
+        if only_set and name != only_set:
+            continue
         keys = sets[name]
         n = keys.shape[0]
         nbr, npairs = ops.kernel_map_k3(keys, ops.HashTable(keys), count_pairs=True)
         pairs = int(npairs.item())
         print(f"== {name}: rows {n} pairs {pairs}", flush=True)
         for cin, cout in shapes:
+            if only_shape and f"{cin}x{cout}" != only_shape:
+                continue
             x = (torch.randn(n, cin, generator=g) * 2).to(dev)
             w = (torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)).to(dev)
             b = torch.randn(1, cout, generator=g).to(dev)
@@ -67,6 +73,9 @@ def main():
             pw = ops.PackedK3Wide(w)
             want_h = cout % 4 == 0
             t_wide = timeit(lambda: ops.conv_k3_wide(xh, nbr, pw, b, relu=True, want_h2=want_h), args.reps)
+            if args.only:
+                print(f"  {cin}->{cout} tcgen05 {t_wide:.4f} ms", flush=True)
+                continue
             y_wide = ops.conv_k3_wide(xh, nbr, pw, b, relu=True)[0]
             t_h2, y_h2 = None, None
             if cin % 16 == 0 and ops.PackedK3H2.supported(cin, cout):

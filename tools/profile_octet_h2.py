@@ -16,6 +16,7 @@ ap.add_argument("--shapes", default="16x16,16x4,16x1,16x32")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--level", type=int, default=2)
 ap.add_argument("--only", default="", help="run only this kernel family (octet_h2) -- for ncu captures")
+ap.add_argument("--h2out", action="store_true", help="write the h2 copy too, as the production path does for decoder.conv2")
 args = ap.parse_args()
 cache = "/tmp/vox10_seed0.npy"
 if os.path.exists(cache): pts = np.load(cache)
@@ -54,8 +55,16 @@ for shape in args.shapes.split(","):
     ph = ops.PackedK3H2(w)
     xh = ops.split_h2(f)
     alg = 4 * (n * cin + n * cout) + 8 * pairs + 4 * 27 * cin * cout
-    ms = timeit(lambda: ops.conv_k3_octet_h2(xh, pnbr, ph, b, relu=True))
+    h2o = args.h2out and cout % 4 == 0
+    ms = timeit(lambda: ops.conv_k3_octet_h2(xh, pnbr, ph, b, relu=True, want_h2=h2o))
     line = f"{shape:8s} octet-h2 {ms:.4f} ms  alg {alg / 1e6:.1f} MB  {alg / ms / 1e6:.1f} GB/s  {2 * pairs * cin * cout / ms / 1e9:.2f} TFLOP/s"
+    if ops.PackedK3OctetTc05.supported(cin, cout):
+        pt = ops.PackedK3OctetTc05(w)
+        ms_t = timeit(lambda: ops.conv_k3_octet_tc05(xh, pnbr, pt, b, relu=True, want_h2=h2o))
+        ref_t = ops.conv_k3_octet_h2(xh, pnbr, ph, b, relu=True)[0]
+        got_t = ops.conv_k3_octet_tc05(xh, pnbr, pt, b, relu=True)[0]
+        line += (f"   octet-tcgen05 {ms_t:.4f} ms ({ms / ms_t:.2f}x, {alg / ms_t / 1e6:.0f} GB/s alg, diff "
+                 f"{float((got_t - ref_t).abs().max() / ref_t.abs().max()):.1e})")
     if not args.only:
         if cout % 4 == 0:
             line += f"  (+h2 out {timeit(lambda: ops.conv_k3_octet_h2(xh, pnbr, ph, b, relu=True, want_h2=True)):.4f})"
