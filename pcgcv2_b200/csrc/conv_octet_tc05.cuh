@@ -10,7 +10,7 @@
 //
 // i.e. for one halo position and one K chunk the eight octets of a group are 128 contiguous bytes -- exactly one 8-row x
 // 16-byte "core matrix" of the canonical K-major (no-swizzle) UMMA layout, with LBO = 128 (next K chunk) and
-// SBO = E = 128 KC (next octet group, and -- four groups on -- the next px).  For a fixed (cy, cz, d) the 64 rows
+// SBO = E (next octet group, and -- four groups on -- the next px; E = KC x 144: 16 bytes of padding per chunk).  For a fixed (cy, cz, d) the 64 rows
 // (cx, o) therefore form ONE valid M = 64 operand: row group rg = 4 cx + grp sits at base + rg E, because
 // px = cx + dx + 1 advances the address by exactly 4 E.  The kernel offset is nothing but a different descriptor start
 // address: 27 offsets x 4 (cy, cz) combinations x CIN/8 K steps = 216 tcgen05.mma (M 64, N 2 cout, K 16) per tile and not a
@@ -54,10 +54,15 @@ struct OCfg {
     static constexpr int TO = 32;                           // octets per tile (4 groups of 8)
     static constexpr int KC = CIN / 4;                      // 16-byte chunks per h2 row
     static constexpr int KSTEPS = KC / 2;                   // tcgen05.mma (K = 16 f16 = two chunks) per offset
-    static constexpr int E = KC * 128;                      // bytes of one (position, group): 8 octets x the whole row
+    // bytes between the K chunks of a (position, group) block: 128 of payload (8 octets x 16 bytes) + 16 of padding, so that the
+    // four chunks of ONE source row (which arrive together from L2 and are written together) fall into four different bank
+    // quads (measured without the padding: 21.5 M shared-memory bank conflicts of the cp.async writes per launch)
+    static constexpr int LBO_A = 144;
+    static constexpr int E = KC * LBO_A;                    // bytes of one (position, group): 8 octets x the whole row
+    static constexpr int EB = KC * 128;                     // the same for the weight tiles (bulk-copied: no padding needed)
     static constexpr int PLANE_BYTES = 16 * 4 * E;          // one z-plane of the halo: 16 positions x 4 groups
     static constexpr int NP = COUT < 8 ? 8 : COUT, N2 = 2 * NP, EW = NP >= 16 ? 16 : 8;
-    static constexpr int B_BYTES = N2 / 8 * E;              // weight tile of one offset: [N2 rows][2 CIN f16], canonical layout
+    static constexpr int B_BYTES = N2 / 8 * EB;             // weight tile of one offset: [N2 rows][2 CIN f16], canonical layout
     static constexpr int W_BYTES = 27 * B_BYTES;
     static constexpr int NG = 3, NBUF = 2;                  // accumulator groups (one per dz) and buffers
     static constexpr int ACC_COLS = 2 * NG * N2;            // per buffer: [cz][dz group][main | small]; cy = the lane half
@@ -173,7 +178,7 @@ conv_k3_octet_tc05_kernel(const uint32_t *__restrict__ in, int in_ld, const int3
                         const int nd = (ndz + 1) * 9 + (ndy + 1) * 3 + (ndx + 1), child = ix + 2 * iy + 4 * iz;
                         const int32_t par = idx_t[nd * TO + 8 * grp + j];
                         const uint32_t *src = in + ((int64_t)(par < 0 ? 0 : par) * 8 + child) * in_ld + 4 * kc;
-                        wide::cp_async16_zfill(plane_s + (pos * 4 + grp) * E + kc * 128 + j * 16, src, par >= 0);
+                        wide::cp_async16_zfill(plane_s + (pos * 4 + grp) * E + kc * C::LBO_A + j * 16, src, par >= 0);
                     }
                 }
                 wide::cp_async_commit();
@@ -189,43 +194,52 @@ conv_k3_octet_tc05_kernel(const uint32_t *__restrict__ in, int in_ld, const int3
         wide::cp_async_wait<0>();
     } else if (warp >= C::MMA_WARP0) {
         // =========================== MMA issuers: warp MMA_WARP0 + cy issues the (cy, *) combinations ===========================
-        const int cy = warp - C::MMA_WARP0;
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(64, N2);
-            mbar_wait(w_ready, 0);
-            const uint32_t w_s = smem_u32(sm + C::OFF_W);
-            for (uint32_t titer = 0; titer < my_tiles; ++titer) {
-                const int buf = titer % NBUF;
-                mbar_wait(tmem_empty + buf, ((titer / NBUF) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + ((uint32_t)(16 * cy) << 16) + buf * C::ACC_COLS;
+        // The whole warp runs this loop converged and one ELECTED lane issues: every operand (descriptors, TMEM addresses) is
+        // then provably warp-uniform and stays in uniform registers -- issued from a lone `lane == 0` branch each tcgen05.mma
+        // cost ~18 instructions of register -> uniform-register moves and an elect loop (measured: the two issuing threads
+        // were busy 75 % of the time while the tensor pipe was 20 % active).
+        const int cy = __shfl_sync(0xffffffffu, warp - C::MMA_WARP0, 0);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        constexpr uint32_t idesc = umma_idesc_f16(64, N2);
+        mbar_wait(w_ready, 0);
+        const uint32_t w_s = smem_u32(sm + C::OFF_W), halo_s = smem_u32(sm + C::OFF_HALO);
+        const uint64_t desc_a = umma_desc_none(0, C::LBO_A, E), desc_b = umma_desc_none(0, 128, C::EB);   // all but the start address
+        for (uint32_t titer = 0; titer < my_tiles; ++titer) {
+            const uint32_t buf = titer % NBUF;
+            mbar_wait(tmem_empty + buf, ((titer / NBUF) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem_u + ((uint32_t)(16 * cy) << 16) + buf * C::ACC_COLS;
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    mbar_wait(full + p, titer & 1);                          // plane p of this tile has landed
-                    tc_fence_after();
-                    const uint32_t plane_s = smem_u32(sm + C::OFF_HALO + (size_t)p * C::PLANE_BYTES);
+            for (int p = 0; p < 4; ++p) {
+                mbar_wait(full + p, titer & 1);                              // plane p of this tile has landed
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t plane_s = halo_s + p * C::PLANE_BYTES;
 #pragma unroll
                     for (int cz = 0; cz < 2; ++cz) {
                         const int dz = p - 1 - cz;                           // cz + dz + 1 == p
                         if (dz < -1 || dz > 1) continue;
                         const uint32_t d = d0 + (cz * NG + (dz + 1)) * N2;
 #pragma unroll
-                        for (int dy = -1; dy <= 1; ++dy)
+                        for (int dy = -1; dy <= 1; ++dy) {
+                            const uint32_t row_s = plane_s + (uint32_t)((cy + dy + 1) * 16) * E;
 #pragma unroll
                             for (int dx = -1; dx <= 1; ++dx) {
                                 const int k = (dz + 1) * 9 + (dy + 1) * 3 + (dx + 1);
-                                const uint32_t a_s = plane_s + (((cy + dy + 1) * 4 + (dx + 1)) * 4) * E;
-                                const uint32_t b_s = w_s + k * C::B_BYTES;
+                                const uint64_t adesc = desc_a | (uint64_t)(((row_s + (dx + 1) * 4 * E) & 0x3FFFF) >> 4);
+                                const uint64_t bdesc = desc_b | (uint64_t)(((w_s + k * C::B_BYTES) & 0x3FFFF) >> 4);
 #pragma unroll
-                                for (int ks = 0; ks < C::KSTEPS; ++ks)
-                                    umma_f16(d, umma_desc_none(a_s + 256 * ks, 128, E), umma_desc_none(b_s + 256 * ks, 128, E), idesc,
-                                             !(dy == -1 && dx == -1 && ks == 0));
+                                for (int ks = 0; ks < C::KSTEPS; ++ks)                      // two K chunks on
+                                    umma_f16(d, adesc + (2 * C::LBO_A / 16) * ks, bdesc + 16 * ks, idesc, !(dy == -1 && dx == -1 && ks == 0));
                             }
+                        }
                     }
                     umma_commit(empty + p);                                  // plane reusable when these MMAs retire
                 }
-                umma_commit(tmem_full + buf);
+                __syncwarp();
             }
+            if (elect_one_sync()) umma_commit(tmem_full + buf);
+            __syncwarp();
         }
     } else {
         // =========================== EPILOGUE warps ===========================

@@ -57,6 +57,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     } while (!ok);
 }
+// one lane of a converged warp (the others fall through): lets the compiler keep warp-uniform operands of the elected lane's
+// tcgen05 instructions in uniform registers instead of moving them there one by one
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -344,21 +351,28 @@ conv_k3_wide_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *_
         }
     } else if (warp == C::MMA_WARP) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(TM, N2);
-            uint32_t g = 0;
-            int titer = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
-                const int buf = titer % NBUF;
-                mbar_wait(tmem_empty + buf, ((titer / NBUF) & 1) ^ 1);       // the epilogue has drained this buffer
+        // The whole warp runs the loop converged and one ELECTED lane issues, so that descriptors and TMEM addresses are
+        // provably warp-uniform and live in uniform registers (a lone `lane == 0` branch costs ~18 instructions of
+        // register -> uniform-register moves plus an elect loop per tcgen05.mma: the issuing thread, not the tensor pipe,
+        // was the bottleneck of the first version -- profiles/r02_octet_tcgen05_v1_ncu.txt).
+        constexpr uint32_t idesc = umma_idesc_f16(TM, N2);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t stage0 = smem_u32(sm + C::OFF_STAGE);
+        const uint64_t desc0 = umma_desc_sw<RB>(0);                          // everything but the start address
+        uint32_t g = 0;
+        int titer = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++titer) {
+            const int buf = titer % NBUF;
+            mbar_wait(tmem_empty + buf, ((titer / NBUF) & 1) ^ 1);           // the epilogue has drained this buffer
+            tc_fence_after();
+            const uint32_t d0 = tmem_u + buf * C::ACC_COLS;
+            for (int k = 0; k < 27; ++k, ++g) {
+                const uint32_t slot = g % S, ph = (g / S) & 1;
+                mbar_wait(full + slot, ph);                                  // gathered rows + weight tile have landed
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + buf * C::ACC_COLS;
-                for (int k = 0; k < 27; ++k, ++g) {
-                    const uint32_t slot = g % S, ph = (g / S) & 1;
-                    mbar_wait(full + slot, ph);                              // gathered rows + weight tile have landed
-                    tc_fence_after();
-                    const uint32_t a_s = smem_u32(sm + C::OFF_STAGE + (size_t)slot * C::STAGE_BYTES), b_s = a_s + C::A_BYTES;
-                    const uint64_t adesc = umma_desc_sw<RB>(a_s), bdesc = umma_desc_sw<RB>(b_s);
+                if (elect_one_sync()) {
+                    const uint32_t a_s = stage0 + slot * C::STAGE_BYTES, b_s = a_s + C::A_BYTES;
+                    const uint64_t adesc = desc0 | (uint64_t)((a_s & 0x3FFFF) >> 4), bdesc = desc0 | (uint64_t)((b_s & 0x3FFFF) >> 4);
                     const int grp = C::group_of(k);
                     const bool first = k == 0 || C::group_of(k - 1) != grp;
                     const uint32_t d = d0 + grp * N2;
@@ -370,8 +384,10 @@ conv_k3_wide_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *_
                                      idesc, !(first && kb == 0 && j == 0));
                     umma_commit(empty + slot);                               // stage reusable when these MMAs retire
                 }
-                umma_commit(tmem_full + buf);                                // accumulators of this tile complete
+                __syncwarp();
             }
+            if (elect_one_sync()) umma_commit(tmem_full + buf);              // accumulators of this tile complete
+            __syncwarp();
         }
     } else {
         // =========================== EPILOGUE warps (warp w owns TMEM lanes 32 w .. 32 w + 31) ===========================
