@@ -421,6 +421,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=2, help="frames in flight per GPU (1 = one frame at a time)")
+    ap.add_argument("--workload", default="codec", choices=["codec", "train"],
+                    help="codec = BASELINE's headline (default); train = the config-5 training step (tools/bench_train.py)")
+    ap.add_argument("--batch", type=int, default=32, help="--workload train: samples per rank and step")
     ap.add_argument("--same-frames", action="store_true", help="every rank codes rank 0's cloud (no frame-size variance between ranks)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -430,6 +433,10 @@ def main():
         if args.steps == 20 and args.warmup == 3:           # defaults sized for the GPU arm; keep the CPU arm bounded
             args.steps, args.warmup = 2, 1
         run_reference(args, rank, world)
+    elif args.workload == "train":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_train
+        bench_train.run(args, rank, world, local_rank)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args, rank, world, local_rank)

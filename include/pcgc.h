@@ -294,22 +294,28 @@ int pcgc_irn_fwd(const pcgc_irn_args *args, void *stream);
  * transposed weights (offset-flipped for k=3: W'[k] = W[26-k]^T; stride-1 kernel maps are symmetric),
  * so only the operations without a forward twin are exported here. */
 
+/* Weight and bias gradients are DETERMINISTIC: blocks write partial sums to the caller's workspace
+ * (pcgc_conv_bwd_weight_ws_bytes(n, kvol, cin, cout) with n = the row count the pairs are enumerated over, kvol = 8 for
+ * the two k=2 layers; pcgc_colsum_ws_bytes()) and a second pass adds them in block order -- no atomics. */
+size_t pcgc_conv_bwd_weight_ws_bytes(int64_t n, int32_t kvol, int32_t cin, int32_t cout);
+size_t pcgc_colsum_ws_bytes(void);
 /* grad_weight [kvol][cin][cout] = sum over pairs of in[a]^T (x) grad_out[b]; kvol 27 with the kernel
  * map of pcgc_kernel_map_k3, or kvol 1 with nbr == NULL (k=1 convolution). */
 int pcgc_conv_bwd_weight(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, int32_t kvol,
                          const float *grad_out, int32_t go_ld, int32_t cin, int32_t cout,
-                         float *grad_weight, void *stream);
+                         float *grad_weight, void *ws, size_t ws_bytes, void *stream);
 /* k=2 s=2 down convolution: grad_in[u] = grad_out[parent_of[u]] @ W[key&7]^T, grad_weight [8][cin][cout]
  * (either output may be NULL). */
 int pcgc_conv_k2s2_bwd(const float *in, int32_t in_ld, const uint64_t *in_keys, const int32_t *parent_of,
                        int64_t n_in, const float *grad_out, int32_t go_ld, const float *weight, int32_t cin,
-                       int32_t cout, float *grad_in, int32_t gi_ld, float *grad_weight, void *stream);
+                       int32_t cout, float *grad_in, int32_t gi_ld, float *grad_weight, void *ws, size_t ws_bytes,
+                       void *stream);
 /* generative k=2 s=2 up convolution: grad_in[i] = sum_k grad_out[8i+k] @ W[k]^T, grad_weight [8][cin][cout]. */
 int pcgc_convT_k2s2_bwd(const float *in, int32_t in_ld, int64_t n_in, const float *grad_out, int32_t go_ld,
                         const float *weight, int32_t cin, int32_t cout, float *grad_in, int32_t gi_ld,
-                        float *grad_weight, void *stream);
+                        float *grad_weight, void *ws, size_t ws_bytes, void *stream);
 /* out[c] = sum over rows of x[r][c]  (bias gradients). */
-int pcgc_colsum(const float *x, int32_t ld, int64_t n, int32_t c, float *out, void *stream);
+int pcgc_colsum(const float *x, int32_t ld, int64_t n, int32_t c, float *out, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- selection / pruning (rows a8, a9) --------------------------------------------------- */
 
@@ -351,6 +357,13 @@ int pcgc_eb_cdf_table(const float *params, int32_t channels, int32_t min_v, int3
 int pcgc_eb_round_minmax(const float *feats, int64_t count, int32_t *minmax, void *stream);
 int pcgc_eb_symbols(const float *feats, int64_t count, const int32_t *minmax, int16_t *sym, void *stream);
 
+/* per-symbol coding intervals on the device (section 8b `pcgc_symbol_ranges`; torchac's per-symbol table walk, Appendix
+ * B.2): symbol i is looked up in row (i % n_tables) of the DEVICE uint16 table [n_tables][lp];
+ * ranges[i] = c_low | (c_high - 1) << 16 (c_high = 0x10000 for the last symbol).  *bad is set to 1 if a symbol lies outside
+ * [0, lp-2] (caller zero-initialises).  pcgc_rc_encode_ranges_host() below codes such a list without touching a table. */
+int pcgc_symbol_ranges(const int16_t *sym, int64_t n_sym, const uint16_t *cdf_u16, int32_t n_tables, int32_t lp,
+                       uint32_t *ranges, int32_t *bad, void *stream);
+
 /* ---- range coder (row a15; HOST functions, synchronous) ----------------------------------
  * torchac.encode_float_cdf / decode_float_cdf -- entropy_model.py:174,192.
  * cdf_float_host: float32 [n_tables][lp]; symbol i is coded with table row (i % n_tables)
@@ -360,6 +373,8 @@ int64_t pcgc_rc_encode_host(const float *cdf_float_host, int64_t n_tables, int32
                             const int16_t *sym_host, int64_t n_sym, uint8_t *out_host, int64_t cap);
 int pcgc_rc_decode_host(const float *cdf_float_host, int64_t n_tables, int32_t lp, const uint8_t *in_host,
                         int64_t in_len, int16_t *sym_host, int64_t n_sym);
+/* the same stream from per-symbol intervals (pcgc_symbol_ranges) */
+int64_t pcgc_rc_encode_ranges_host(const uint32_t *ranges_host, int64_t n_sym, uint8_t *out_host, int64_t cap);
 /* same with a ready uint16 table [n_tables][lp] */
 int64_t pcgc_rc_encode_u16_host(const uint16_t *cdf_u16_host, int64_t n_tables, int32_t lp,
                                 const int16_t *sym_host, int64_t n_sym, uint8_t *out_host, int64_t cap);
@@ -404,6 +419,18 @@ int pcgc_conv_k3_octet_tc05_fwd(const uint32_t *feats_h2, int32_t in_ld, const i
                                 const void *packed, float inv_scale, const float *bias, int32_t cin, int32_t cout,
                                 const float *residual, int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2,
                                 int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream);
+
+/* ---- occupancy loss of the training path (row f4) ----------------------------------------------
+ * get_bce(data, ground_truth) -- loss.py:7-15 (trainer.py:127-130): isin(data.C, ground_truth.C)
+ * fused with BCE-with-logits: for every candidate row the ground-truth table is probed, the
+ * stable binary cross entropy is summed (in bits: / ln 2, i.e. the reference's `sum_bce`) and
+ * grad_unit[i] = (sigmoid(x_i) - t_i) / ln 2 is written for the backward pass (either output
+ * pointer may be NULL; `target` receives the 0/1 mask).  Deterministic two-stage reduction.
+ * logits: float [n] with row stride ld; ws: pcgc_bce_isin_ws_bytes() bytes. */
+size_t pcgc_bce_isin_ws_bytes(void);
+int pcgc_bce_isin(const float *logits, int32_t ld, const uint64_t *cand_keys, int64_t n, const uint64_t *gt_table_keys,
+                  int64_t cap, float *loss_sum_bits, float *grad_unit, uint8_t *target, void *ws, size_t ws_bytes,
+                  void *stream);
 
 /* ---- ASCII PLY geometry I/O (row f2; HOST functions, synchronous) ---------------------------
  * read_ply_ascii_geo / write_ply_ascii_geo -- data_utils.py:19-48 (coder.py:26,33,128,177).

@@ -95,10 +95,13 @@ SIGNATURES = {
     "pcgc_convT_k2s2_fwd_h2out": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_p]),
     "pcgc_irn_ws_bytes": (c_sz, [c_i64, c_i32]),
     "pcgc_irn_fwd": (ctypes.c_int, [c_p, c_p]),
-    "pcgc_conv_bwd_weight": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_i32, c_p, c_p]),
-    "pcgc_conv_k2s2_bwd": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_i64, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_p]),
-    "pcgc_convT_k2s2_bwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_p]),
-    "pcgc_colsum": (ctypes.c_int, [c_p, c_i32, c_i64, c_i32, c_p, c_p]),
+    "pcgc_conv_bwd_weight_ws_bytes": (c_sz, [c_i64, c_i32, c_i32, c_i32]),
+    "pcgc_colsum_ws_bytes": (c_sz, []),
+    "pcgc_conv_bwd_weight": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_i32, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_sz, c_p]),
+    "pcgc_conv_k2s2_bwd": (ctypes.c_int, [c_p, c_i32, c_p, c_p, c_i64, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_p,
+                                          c_sz, c_p]),
+    "pcgc_convT_k2s2_bwd": (ctypes.c_int, [c_p, c_i32, c_i64, c_p, c_i32, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_p, c_sz, c_p]),
+    "pcgc_colsum": (ctypes.c_int, [c_p, c_i32, c_i64, c_i32, c_p, c_p, c_sz, c_p]),
     "pcgc_topk_mask_ws_bytes": (c_sz, [c_i64]),
     "pcgc_topk_mask": (ctypes.c_int, [c_p, c_i32, c_i64, c_i64, c_p, c_p, c_sz, c_p]),
     "pcgc_prune_ws_bytes": (c_sz, [c_i64]),
@@ -112,6 +115,10 @@ SIGNATURES = {
     "pcgc_rc_decode_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
     "pcgc_rc_encode_u16_host": (c_i64, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
     "pcgc_rc_decode_u16_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
+    "pcgc_symbol_ranges": (ctypes.c_int, [c_p, c_i64, c_p, c_i32, c_i32, c_p, c_p, c_p]),
+    "pcgc_rc_encode_ranges_host": (c_i64, [c_p, c_i64, c_p, c_i64]),
+    "pcgc_bce_isin_ws_bytes": (c_sz, []),
+    "pcgc_bce_isin": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "pcgc_d1_sqdist": (ctypes.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i32, c_p, c_p, c_p]),
     "pcgc_ply_count_lines_host": (c_i64, [c_p, c_i64]),
     "pcgc_ply_parse_ascii_host": (c_i64, [c_p, c_i64, c_p, c_i64]),

@@ -6,8 +6,9 @@
 //   the transposed, offset-flipped weights.  This file holds what has no forward twin:
 //     * weight gradients  gW[k] = sum over pairs (a, b) of  A[a]^T (x) G[b]   (all four conv types),
 //     * input gradients of the k=2 s=2 down conv and the generative k=2 s=2 up conv.
-//   First implementation: generic in the channel counts, FP32 FFMA, shared-memory row tiles, one
-//   atomicAdd per weight element per block.  Training shapes (64^3 crops, batch 8-32) are small.
+//   Generic in the channel counts, FP32 FFMA, shared-memory row tiles.  DETERMINISTIC: every block writes its partial
+//   [kvol][ca][cb] sums to the caller's workspace and a second pass adds the partials in block order (no atomics), so the
+//   gradients -- and with them a data-parallel run's all-reduced update -- are bit-reproducible.
 #include "common.cuh"
 
 namespace pcgc {
@@ -24,7 +25,7 @@ __global__ void __launch_bounds__(256)
 weight_grad_kernel(int mode, const float *__restrict__ A, int a_ld, const float *__restrict__ B, int b_ld,
                    const int32_t *__restrict__ nbr, const int32_t *__restrict__ parent_of,
                    const uint64_t *__restrict__ keys, int64_t n, int ca, int cb, int rows_per_block,
-                   float *__restrict__ gw) {
+                   float *__restrict__ partial) {
     constexpr int TR = 16;
     extern __shared__ float sm[];
     float *as = sm;                    // [TR][ca]
@@ -76,7 +77,16 @@ weight_grad_kernel(int mode, const float *__restrict__ A, int a_ld, const float 
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int idx = threadIdx.x + e * 256;
-        if (idx < total && acc[e] != 0.f) atomicAdd(gw + (int64_t)k * total + idx, acc[e]);
+        if (idx < total) partial[((int64_t)blockIdx.x * gridDim.y + k) * total + idx] = acc[e];
+    }
+}
+
+// out[i] = partial[0][i] + partial[1][i] + ... in block order
+__global__ void sum_partials_kernel(const float *__restrict__ partial, int blocks, int64_t count, float *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int b = 0; b < blocks; ++b) s += partial[(int64_t)b * count + i];
+        out[i] = s;
     }
 }
 
@@ -113,30 +123,59 @@ __global__ void up_bwd_data_kernel(const float *__restrict__ go, int go_ld, int6
     }
 }
 
-// out[c] += sum_rows x[r][c]  (bias gradients)
-__global__ void colsum_kernel(const float *__restrict__ x, int ld, int64_t n, int c, float *__restrict__ out) {
+// partial[block][c] = sum over the block's rows of x[r][c]  (bias gradients; summed in block order by sum_partials_kernel)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float *__restrict__ x, int ld, int64_t n, int c, float *__restrict__ partial) {
+    __shared__ float red[256];
     const int col = threadIdx.x % c, lane_row = threadIdx.x / c, rows_per_iter = blockDim.x / c;
-    if (lane_row >= rows_per_iter) return;
     float s = 0.f;
-    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + lane_row; r < n; r += (int64_t)gridDim.x * rows_per_iter)
-        s += x[r * ld + col];
-    atomicAdd(out + col, s);
+    if (lane_row < rows_per_iter)
+        for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + lane_row; r < n; r += (int64_t)gridDim.x * rows_per_iter)
+            s += x[r * ld + col];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < c) {
+        float t = 0.f;
+        for (int j = 0; j < rows_per_iter; ++j) t += red[j * c + threadIdx.x];
+        partial[(int64_t)blockIdx.x * c + threadIdx.x] = t;
+    }
+}
+
+constexpr int kColsumBlocks = 2 * kNumSMs;
+
+static int weight_grad_rows_per_block(int64_t n) {          // at most 256 partial blocks per kernel offset
+    int64_t r = (n + 255) / 256;
+    r = (r + 15) / 16 * 16;
+    return (int)(r < 2048 ? 2048 : r);
+}
+static size_t weight_grad_ws_bytes(int64_t n, int kvol, int ca, int cb) {
+    if (n <= 0) return 0;
+    const int rpb = weight_grad_rows_per_block(n);
+    return sizeof(float) * (size_t)((n + rpb - 1) / rpb) * kvol * ca * cb;
 }
 
 static int launch_weight_grad(int mode, const float *A, int a_ld, const float *B, int b_ld, const int32_t *nbr,
                               const int32_t *parent_of, const uint64_t *keys, int64_t n, int kvol, int ca, int cb,
-                              float *gw, cudaStream_t s) {
+                              float *gw, void *ws, size_t ws_bytes, cudaStream_t s) {
     PCGC_REQUIRE(ca >= 1 && cb >= 1 && ca * cb <= 256 * 64, "weight gradient: %dx%d channels not supported", ca, cb);
-    PCGC_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)kvol * ca * cb, s));
-    if (n == 0) return PCGC_OK;
-    const int rows_per_block = 2048;
+    if (n == 0) {
+        PCGC_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)kvol * ca * cb, s));
+        return PCGC_OK;
+    }
+    PCGC_REQUIRE(ws && ws_bytes >= weight_grad_ws_bytes(n, kvol, ca, cb), "weight gradient: workspace too small");
+    const int rows_per_block = weight_grad_rows_per_block(n);
     dim3 grid((unsigned)((n + rows_per_block - 1) / rows_per_block), kvol);
+    float *part = (float *)ws;
     const size_t smem = sizeof(float) * 16 * (ca + cb);
     const int e = (ca * cb + 255) / 256;
-#define WG(E) weight_grad_kernel<E><<<grid, 256, smem, s>>>(mode, A, a_ld, B, b_ld, nbr, parent_of, keys, n, ca, cb, rows_per_block, gw)
+#define WG(E) weight_grad_kernel<E><<<grid, 256, smem, s>>>(mode, A, a_ld, B, b_ld, nbr, parent_of, keys, n, ca, cb, rows_per_block, part)
     if (e <= 1) WG(1); else if (e <= 4) WG(4); else if (e <= 16) WG(16); else WG(64);
 #undef WG
-    return check_launch("weight_grad");
+    int rc = check_launch("weight_grad");
+    if (rc) return rc;
+    const int64_t count = (int64_t)kvol * ca * cb;
+    sum_partials_kernel<<<grid_for(count, 256, 4), 256, 0, s>>>(part, (int)grid.x, count, gw);
+    return check_launch("weight_grad_sum");
 }
 
 }  // namespace pcgc
@@ -145,22 +184,28 @@ using namespace pcgc;
 
 extern "C" {
 
+size_t pcgc_conv_bwd_weight_ws_bytes(int64_t n, int32_t kvol, int32_t cin, int32_t cout) {
+    return weight_grad_ws_bytes(n, kvol, cin, cout);
+}
+
+size_t pcgc_colsum_ws_bytes(void) { return sizeof(float) * kColsumBlocks * 256; }
+
 int pcgc_conv_bwd_weight(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, int32_t kvol,
                          const float *grad_out, int32_t go_ld, int32_t cin, int32_t cout, float *grad_weight,
-                         void *stream) {
+                         void *ws, size_t ws_bytes, void *stream) {
     PCGC_REQUIRE((kvol == 27 && nbr) || (kvol == 1 && !nbr), "pcgc_conv_bwd_weight: kvol 27 needs a kernel map, kvol 1 none");
     return launch_weight_grad(kvol == 27 ? PAIR_K3 : PAIR_IDENT, in, in_ld, grad_out, go_ld, nbr, nullptr, nullptr, n, kvol,
-                              cin, cout, grad_weight, (cudaStream_t)stream);
+                              cin, cout, grad_weight, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int pcgc_conv_k2s2_bwd(const float *in, int32_t in_ld, const uint64_t *in_keys, const int32_t *parent_of, int64_t n_in,
                        const float *grad_out, int32_t go_ld, const float *weight, int32_t cin, int32_t cout,
-                       float *grad_in, int32_t gi_ld, float *grad_weight, void *stream) {
+                       float *grad_in, int32_t gi_ld, float *grad_weight, void *ws, size_t ws_bytes, void *stream) {
     PCGC_REQUIRE(in_keys && parent_of, "pcgc_conv_k2s2_bwd: null map");
     cudaStream_t s = (cudaStream_t)stream;
     if (grad_weight) {
         int rc = launch_weight_grad(PAIR_DOWN, in, in_ld, grad_out, go_ld, nullptr, parent_of, in_keys, n_in, 8, cin, cout,
-                                    grad_weight, s);
+                                    grad_weight, ws, ws_bytes, s);
         if (rc) return rc;
     }
     if (grad_in && n_in) {
@@ -173,11 +218,11 @@ int pcgc_conv_k2s2_bwd(const float *in, int32_t in_ld, const uint64_t *in_keys, 
 
 int pcgc_convT_k2s2_bwd(const float *in, int32_t in_ld, int64_t n_in, const float *grad_out, int32_t go_ld,
                         const float *weight, int32_t cin, int32_t cout, float *grad_in, int32_t gi_ld,
-                        float *grad_weight, void *stream) {
+                        float *grad_weight, void *ws, size_t ws_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (grad_weight) {
         int rc = launch_weight_grad(PAIR_UP, in, in_ld, grad_out, go_ld, nullptr, nullptr, nullptr, n_in, 8, cin, cout,
-                                    grad_weight, s);
+                                    grad_weight, ws, ws_bytes, s);
         if (rc) return rc;
     }
     if (grad_in && n_in) {
@@ -188,14 +233,22 @@ int pcgc_convT_k2s2_bwd(const float *in, int32_t in_ld, int64_t n_in, const floa
     return PCGC_OK;
 }
 
-int pcgc_colsum(const float *x, int32_t ld, int64_t n, int32_t c, float *out, void *stream) {
+int pcgc_colsum(const float *x, int32_t ld, int64_t n, int32_t c, float *out, void *ws, size_t ws_bytes, void *stream) {
     PCGC_REQUIRE(c >= 1 && c <= 256 && ld >= c, "pcgc_colsum: bad shape");
     cudaStream_t s = (cudaStream_t)stream;
-    PCGC_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * c, s));
-    if (n == 0) return PCGC_OK;
+    if (n == 0) {
+        PCGC_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * c, s));
+        return PCGC_OK;
+    }
+    PCGC_REQUIRE(ws && ws_bytes >= pcgc_colsum_ws_bytes(), "pcgc_colsum: workspace too small");
     const int rows_per_iter = 256 / c;
-    colsum_kernel<<<grid_for(n, rows_per_iter * 8, 2), 256, 0, s>>>(x, ld, n, c, out);
-    return check_launch("colsum");
+    int blocks = grid_for(n, rows_per_iter * 8, 2);
+    if (blocks > kColsumBlocks) blocks = kColsumBlocks;
+    colsum_kernel<<<blocks, 256, 0, s>>>(x, ld, n, c, (float *)ws);
+    int rc = check_launch("colsum");
+    if (rc) return rc;
+    sum_partials_kernel<<<1, 256, 0, s>>>((const float *)ws, blocks, c, out);
+    return check_launch("colsum_sum");
 }
 
 }  // extern "C"

@@ -273,6 +273,19 @@ __global__ void eb_symbols_kernel(const float *__restrict__ x, int64_t count, co
         sym[i] = (int16_t)((int)rintf(__ldg(x + i)) - lo);
 }
 
+// per-symbol coding interval of the range coder (Appendix B.2): symbol i uses table row i % n_tables;
+// ranges[i] = c_low | (c_high - 1) << 16 with c_high = 0x10000 for the last symbol of the alphabet
+__global__ void symbol_ranges_kernel(const int16_t *__restrict__ sym, int64_t n, const uint16_t *__restrict__ cdf, int n_tables,
+                                     int lp, uint32_t *__restrict__ ranges, int32_t *__restrict__ bad) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int s = sym[i];
+        if (s < 0 || s > lp - 2) { *bad = 1; ranges[i] = 0; continue; }
+        const uint16_t *row = cdf + (i % n_tables) * lp;
+        const uint32_t lo = row[s], hi = s == lp - 2 ? 0x10000u : row[s + 1];
+        ranges[i] = lo | ((hi - 1u) << 16);
+    }
+}
+
 }  // namespace pcgc
 
 using namespace pcgc;
@@ -316,6 +329,14 @@ int pcgc_eb_round_minmax(const float *feats, int64_t count, int32_t *minmax, voi
     if (count == 0) return PCGC_OK;
     eb_round_minmax_kernel<<<grid_for(count, 256, 4), 256, 0, (cudaStream_t)stream>>>(feats, count, minmax);
     return check_launch("eb_round_minmax");
+}
+
+int pcgc_symbol_ranges(const int16_t *sym, int64_t n_sym, const uint16_t *cdf_u16, int32_t n_tables, int32_t lp,
+                       uint32_t *ranges, int32_t *bad, void *stream) {
+    PCGC_REQUIRE(n_sym >= 0 && n_tables >= 1 && lp >= 2 && cdf_u16 && bad, "pcgc_symbol_ranges: bad arguments");
+    if (n_sym == 0) return PCGC_OK;
+    symbol_ranges_kernel<<<grid_for(n_sym, 256, 4), 256, 0, (cudaStream_t)stream>>>(sym, n_sym, cdf_u16, n_tables, lp, ranges, bad);
+    return check_launch("symbol_ranges");
 }
 
 int pcgc_eb_symbols(const float *feats, int64_t count, const int32_t *minmax, int16_t *sym, void *stream) {

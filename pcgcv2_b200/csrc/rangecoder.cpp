@@ -94,22 +94,9 @@ struct Interval {
     }
 };
 
-int64_t encode_u16(const uint16_t *cdf, int64_t n_tables, int32_t lp, const int16_t *sym, int64_t n_sym, uint8_t *out,
-                   int64_t cap) {
-    BitSink sink(out, cap);
-    Interval iv;
-    uint64_t pending = 0;
-    const int32_t max_symbol = lp - 2;
-    int64_t t = 0;
-    for (int64_t i = 0; i < n_sym; ++i) {
-        const uint16_t *row = cdf + t * lp;
-        if (++t == n_tables) t = 0;
-        const int32_t s = sym[i];
-        if (s < 0 || s > max_symbol) {
-            pcgc::set_error("pcgc_rc_encode: symbol %d at %lld outside [0, %d]", s, (long long)i, max_symbol);
-            return PCGC_ERR_RANGE;
-        }
-        iv.narrow(row[s], s == max_symbol ? 0x10000u : row[s + 1]);
+// one coding step of Appendix B.2: narrow to [c_low, c_high) / 2^16, then renormalise
+static inline void encode_step(Interval &iv, BitSink &sink, uint64_t &pending, uint32_t c_low, uint32_t c_high) {
+        iv.narrow(c_low, c_high);
         for (;;) {
             if (iv.high < kHalf) {
                 sink.put_with_pending(0, pending);
@@ -126,6 +113,41 @@ int64_t encode_u16(const uint16_t *cdf, int64_t n_tables, int32_t lp, const int1
             iv.low <<= 1;
             iv.high = (iv.high << 1) | 1u;
         }
+}
+
+int64_t encode_u16(const uint16_t *cdf, int64_t n_tables, int32_t lp, const int16_t *sym, int64_t n_sym, uint8_t *out,
+                   int64_t cap) {
+    BitSink sink(out, cap);
+    Interval iv;
+    uint64_t pending = 0;
+    const int32_t max_symbol = lp - 2;
+    int64_t t = 0;
+    for (int64_t i = 0; i < n_sym; ++i) {
+        const uint16_t *row = cdf + t * lp;
+        if (++t == n_tables) t = 0;
+        const int32_t s = sym[i];
+        if (s < 0 || s > max_symbol) {
+            pcgc::set_error("pcgc_rc_encode: symbol %d at %lld outside [0, %d]", s, (long long)i, max_symbol);
+            return PCGC_ERR_RANGE;
+        }
+        encode_step(iv, sink, pending, row[s], s == max_symbol ? 0x10000u : row[s + 1]);
+    }
+    ++pending;
+    sink.put_with_pending(iv.low < kQuarter ? 0u : 1u, pending);
+    return sink.finish();
+}
+
+int64_t encode_ranges(const uint32_t *ranges, int64_t n_sym, uint8_t *out, int64_t cap) {
+    BitSink sink(out, cap);
+    Interval iv;
+    uint64_t pending = 0;
+    for (int64_t i = 0; i < n_sym; ++i) {
+        const uint32_t r = ranges[i], c_low = r & 0xFFFFu, c_high = (r >> 16) + 1u;
+        if (c_high <= c_low) {
+            pcgc::set_error("pcgc_rc_encode_ranges: empty interval at %lld", (long long)i);
+            return PCGC_ERR_RANGE;
+        }
+        encode_step(iv, sink, pending, c_low, c_high);
     }
     ++pending;
     sink.put_with_pending(iv.low < kQuarter ? 0u : 1u, pending);
@@ -179,6 +201,14 @@ bool bad_args(const void *cdf, int64_t n_tables, int32_t lp, const void *sym, in
 }  // namespace
 
 extern "C" {
+
+int64_t pcgc_rc_encode_ranges_host(const uint32_t *ranges_host, int64_t n_sym, uint8_t *out_host, int64_t cap) {
+    if (n_sym < 0 || (n_sym > 0 && !ranges_host)) {
+        pcgc::set_error("pcgc_rc_encode_ranges: bad arguments");
+        return PCGC_ERR_INVALID;
+    }
+    return encode_ranges(ranges_host, n_sym, out_host, cap);
+}
 
 int64_t pcgc_rc_encode_u16_host(const uint16_t *cdf_u16_host, int64_t n_tables, int32_t lp, const int16_t *sym_host,
                                 int64_t n_sym, uint8_t *out_host, int64_t cap) {

@@ -654,9 +654,16 @@ def conv_bwd_weight(feats, nbr, grad_out, kvol, cin, cout):
     """grad of `kernel` for k=3 (kvol 27, nbr given) / k=1 (kvol 1, nbr None) -> [kvol, cin, cout]."""
     feats, grad_out = _feat(feats), _feat(grad_out)
     gw = torch.empty((kvol, cin, cout), dtype=torch.float32, device=feats.device)
+    ws, nbytes = _bwd_ws(feats.shape[0], kvol, cin, cout, feats.device)
     check(_lib.lib().pcgc_conv_bwd_weight(_p(feats), feats.stride(0), _p(nbr), feats.shape[0], kvol, _p(grad_out),
-                                          grad_out.stride(0), cin, cout, _p(gw), _stream()), "pcgc_conv_bwd_weight")
+                                          grad_out.stride(0), cin, cout, _p(gw), _p(ws), nbytes, _stream()), "pcgc_conv_bwd_weight")
     return gw
+
+
+def _bwd_ws(n, kvol, cin, cout, device):
+    """workspace of the deterministic two-pass weight gradient (partials per block, summed in block order)."""
+    nbytes = int(_lib.lib().pcgc_conv_bwd_weight_ws_bytes(n, kvol, cin, cout))
+    return _ws(max(nbytes, 16), device), nbytes
 
 
 def conv_k2s2_bwd(feats, in_keys, parent_of, grad_out, weight, need_input_grad=True):
@@ -665,9 +672,10 @@ def conv_k2s2_bwd(feats, in_keys, parent_of, grad_out, weight, need_input_grad=T
     cout = weight.shape[2]
     gi = torch.empty((n, cin), dtype=torch.float32, device=feats.device) if need_input_grad else None
     gw = torch.empty_like(weight)
+    ws, nbytes = _bwd_ws(n, 8, cin, cout, feats.device)
     check(_lib.lib().pcgc_conv_k2s2_bwd(_p(feats), feats.stride(0), _p(in_keys), _p(parent_of), n, _p(grad_out),
-                                        grad_out.stride(0), _p(weight), cin, cout, _p(gi), cin, _p(gw), _stream()),
-          "pcgc_conv_k2s2_bwd")
+                                        grad_out.stride(0), _p(weight), cin, cout, _p(gi), cin, _p(gw), _p(ws), nbytes,
+                                        _stream()), "pcgc_conv_k2s2_bwd")
     return gi, gw
 
 
@@ -677,16 +685,38 @@ def convT_k2s2_bwd(feats, grad_out, weight, need_input_grad=True):
     cout = weight.shape[2]
     gi = torch.empty((n, cin), dtype=torch.float32, device=feats.device) if need_input_grad else None
     gw = torch.empty_like(weight)
+    ws, nbytes = _bwd_ws(n, 8, cin, cout, feats.device)
     check(_lib.lib().pcgc_convT_k2s2_bwd(_p(feats), feats.stride(0), n, _p(grad_out), grad_out.stride(0), _p(weight), cin,
-                                         cout, _p(gi), cin, _p(gw), _stream()), "pcgc_convT_k2s2_bwd")
+                                         cout, _p(gi), cin, _p(gw), _p(ws), nbytes, _stream()), "pcgc_convT_k2s2_bwd")
     return gi, gw
 
 
 def colsum(x):
     x = _feat(x)
     out = torch.empty((1, x.shape[1]), dtype=torch.float32, device=x.device)
-    check(_lib.lib().pcgc_colsum(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(out), _stream()), "pcgc_colsum")
+    nbytes = int(_lib.lib().pcgc_colsum_ws_bytes())
+    ws = _ws(nbytes, x.device)
+    check(_lib.lib().pcgc_colsum(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(out), _p(ws), nbytes, _stream()), "pcgc_colsum")
     return out
+
+
+def bce_isin(logits: torch.Tensor, cand_keys: torch.Tensor, gt_table: "HashTable", need_grad=True):
+    """fused loss.py:7-15: -> (sum of BCE-with-logits over the isin mask in bits, float32 [1] on the device;
+    d(sum)/d(logit) float32 [n] or None; the 0/1 mask uint8 [n])."""
+    _need_cuda(logits, cand_keys)
+    x = logits.reshape(logits.shape[0], -1) if logits.dim() > 1 else logits
+    assert x.dim() == 1 or x.shape[1] == 1, "one logit per candidate row"
+    n = x.shape[0]
+    ld = x.stride(0) if n > 1 else 1
+    L = _lib.lib()
+    loss = torch.empty(1, dtype=torch.float32, device=x.device)
+    grad = torch.empty(n, dtype=torch.float32, device=x.device) if need_grad else None
+    target = torch.empty(n, dtype=torch.uint8, device=x.device)
+    nbytes = int(L.pcgc_bce_isin_ws_bytes())
+    ws = _ws(nbytes, x.device)
+    check(L.pcgc_bce_isin(_p(x), max(int(ld), 1), _p(cand_keys), n, _p(gt_table.tkeys), gt_table.cap, _p(loss), _p(grad), _p(target),
+                          _p(ws), nbytes, _stream()), "pcgc_bce_isin")
+    return loss, grad, target
 
 
 # ------------------------------------------------------------------ selection / pruning
@@ -847,6 +877,35 @@ def rc_encode_u16(table: np.ndarray, sym: np.ndarray) -> bytes:
     if n > cap:
         out = np.empty(n, dtype=np.uint8)
         check(_lib.lib().pcgc_rc_encode_u16_host(table.ctypes.data, T, lp, sym.ctypes.data, sym.size, out.ctypes.data, n))
+    return out[:n].tobytes()
+
+
+def symbol_ranges(sym: torch.Tensor, table_u16: torch.Tensor) -> torch.Tensor:
+    """per-symbol coding intervals on the device (pcgc_symbol_ranges): sym int16 [n] (row-major [N3, C]), table uint16-as-int16
+    [C, L+1] on the same device -> int32 [n] holding c_low | (c_high - 1) << 16.  Raises on symbols outside the alphabet."""
+    _need_cuda(sym, table_u16)
+    sym = sym.contiguous().reshape(-1)
+    assert sym.dtype == torch.int16 and table_u16.dtype in (torch.int16, torch.uint16) and table_u16.dim() == 2
+    table_u16 = table_u16.contiguous()
+    ranges = torch.empty(sym.shape[0], dtype=torch.int32, device=sym.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=sym.device)
+    check(_lib.lib().pcgc_symbol_ranges(_p(sym), sym.shape[0], _p(table_u16), table_u16.shape[0], table_u16.shape[1], _p(ranges),
+                                        _p(bad), _stream()), "pcgc_symbol_ranges")
+    if sym.shape[0] and int(bad.item()):
+        raise ValueError("symbol outside the table's alphabet")
+    return ranges
+
+
+def rc_encode_ranges(ranges: np.ndarray) -> bytes:
+    """the torchac-compatible stream from per-symbol intervals (host; pcgc_rc_encode_ranges_host)."""
+    ranges = np.ascontiguousarray(ranges).view(np.uint32).reshape(-1)
+    cap = 4 * ranges.size + 64
+    out = np.empty(cap, dtype=np.uint8)
+    n = _lib.lib().pcgc_rc_encode_ranges_host(ranges.ctypes.data, ranges.size, out.ctypes.data, cap)
+    check(n, "pcgc_rc_encode_ranges_host")
+    if n > cap:
+        out = np.empty(n, dtype=np.uint8)
+        check(_lib.lib().pcgc_rc_encode_ranges_host(ranges.ctypes.data, ranges.size, out.ctypes.data, n))
     return out[:n].tobytes()
 
 

@@ -202,3 +202,80 @@ def test_training_step_matches_oracle_and_learns(ME):
                    for cls, gt in zip(out2["out_cls_list"], out2["ground_truth_list"]))
         loss2 = bce2 - torch.log2(out2["likelihood"]).sum() / float(len(x))
     assert float(loss2) < float(loss)
+
+
+def test_fused_bce_isin_matches_reference_loss_and_is_deterministic(ME):
+    """row f4: get_bce (one fused pcgc_bce_isin pass) == loss.py:7-15 evaluated with torch (BCEWithLogitsLoss over the
+    isin mask, / ln 2, x rows) in value and gradient; batch index is part of the membership test; the reduction is
+    bit-reproducible; strided logits; empty candidate set."""
+    from pcgcv2_b200 import train
+    from data_utils import isin
+    rng = np.random.default_rng(11)
+    cand = np.unique(rng.integers(0, 24, size=(30000, 4)) % np.array([3, 24, 24, 24]), axis=0).astype(np.int32)
+    gt = cand[rng.random(len(cand)) < 0.3].copy()
+    gt[:50, 0] = (gt[:50, 0] + 1) % 3                                                      # same xyz, other batch item
+    gt = np.unique(gt, axis=0)
+    g = torch.Generator().manual_seed(3)
+    logits = (torch.randn(len(cand), 1, generator=g) * 6).cuda().requires_grad_()            # saturating values included
+    data = ME.SparseTensor(features=logits, coordinates=torch.from_numpy(cand), device="cuda")
+    truth = ME.SparseTensor(features=torch.ones(len(gt), 1), coordinates=torch.from_numpy(gt), device="cuda")
+    got = train.get_bce(data, truth)
+    got.backward()
+    mask = isin(data.C, truth.C)
+    cset = set(map(tuple, gt.tolist()))
+    assert mask.cpu().tolist() == [tuple(r) in cset for r in data.C.cpu().numpy().tolist()]
+    ref_logits = logits.detach().double().requires_grad_()
+    ref = torch.nn.BCEWithLogitsLoss()(ref_logits.squeeze(), mask.double()) / np.log(2.0) * len(cand)
+    ref.backward()
+    assert abs(float(got) - float(ref)) <= 2e-6 * float(ref)
+    assert float((logits.grad.double() - ref_logits.grad).abs().max()) <= 2e-6 * float(ref_logits.grad.abs().max())
+    again = train.get_bce(data, truth)
+    assert float(again) == float(got)                                                       # fixed-order reduction
+    # the reference's own loss.py over the shims (host isin + torch BCE) gives the same number to fp32 rounding
+    crit = torch.nn.BCEWithLogitsLoss()(logits.detach().squeeze(), mask.float()) / np.log(2.0) * len(cand)
+    assert abs(float(got) - float(crit)) <= 1e-5 * float(crit)
+    wide = torch.randn(len(cand), 4, generator=g).cuda()
+    l1, _, t1 = ops.bce_isin(wide[:, 2:3], data.coordinate_manager._get(data.coordinate_map_key).keys,
+                             truth.coordinate_manager._get(truth.coordinate_map_key).table)
+    l2, _, _ = ops.bce_isin(wide[:, 2].contiguous(), data.coordinate_manager._get(data.coordinate_map_key).keys,
+                            truth.coordinate_manager._get(truth.coordinate_map_key).table)
+    assert float(l1) == float(l2) and t1.bool().tolist() == mask.tolist()
+    assert train.get_cls_metrics(mask, mask) == [1.0, 1.0, 1.0]
+
+
+def test_weight_and_bias_gradients_are_bit_reproducible(ME):
+    """a16: the weight / bias gradient kernels add per-block partials in block order -- two runs give identical bits."""
+    c = _cloud(77, n=60000, size=48)
+    g = torch.Generator().manual_seed(8)
+    f = torch.randn(len(c), 16, generator=g).cuda()
+    conv = ME.MinkowskiConvolution(in_channels=16, out_channels=32, kernel_size=3, stride=1, bias=True, dimension=3).cuda()
+    probe = torch.randn(len(c), 32, generator=g).cuda()
+    grads = []
+    for _ in range(3):
+        conv.zero_grad(set_to_none=True)
+        (conv(_sparse(ME, c, f)).F * probe).sum().backward()
+        grads.append((conv.kernel.grad.clone(), conv.bias.grad.clone()))
+    assert all(torch.equal(grads[0][0], k) and torch.equal(grads[0][1], b) for k, b in grads[1:])
+    ref = S.conv_k3(f.cpu().requires_grad_(False), c, 1, conv.kernel.detach().cpu().requires_grad_(), conv.bias.detach().cpu())
+    assert _rel(conv(_sparse(ME, c, f)).F.detach(), ref.detach()) < TOL
+
+
+def test_data_parallel_train_step_single_rank(ME):
+    """train_step (flat gradient bucket, fused losses, Adam) lowers the loss on a config-5 style batch of shells."""
+    from pcgcv2_b200 import train
+    from pcgcv2_b200.model import PCCModel
+    torch.manual_seed(0)
+    model = PCCModel().cuda().train()
+    coords, feats = train.shell_batch(0, batch=4, size=64, rng_points=6000)
+    assert coords[:, 0].max() == 3 and 8000 < len(coords) < 40000
+    x = ME.SparseTensor(features=torch.from_numpy(feats), coordinates=torch.from_numpy(coords), device="cuda")
+    bucket = train.GradBucket(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=train.adam_lr(), betas=(0.9, 0.999))
+    first = last = None
+    for it in range(8):
+        loss, bce, bpp = train.train_step(model, opt, bucket, x)
+        first = float(loss) if first is None else first
+        last = float(loss)
+        assert np.isfinite(last)
+    assert last < first, (first, last)
+    assert model.encoder.conv0.kernel.grad.data_ptr() == bucket.views[model.encoder.conv0.kernel].data_ptr()

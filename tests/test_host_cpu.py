@@ -63,3 +63,47 @@ def test_ply_io_native_matches_reference_semantics(tmp_path):
         fh.write("ply\nformat ascii 1.0\ncomment 1 2 3\nelement vertex 4\nproperty float x\nend_header\n"
                  "1 2 3\n4.7 -5.2 6e0 9 9\n7  8 9\n-1 -2 -3 \n10 11 12")
     assert ops.ply_read_ascii(odd).numpy().tolist() == [[1, 2, 3], [4, -5, 6], [-1, -2, -3], [10, 11, 12]]
+
+
+@pytest.mark.parametrize("name", ["r3", "r7"])
+def test_host_cdf_table_is_exactly_the_references(name):
+    """the table Codec codes with (entropy_host.HostTable: the reference's float32 CPU operator sequence) == the table the
+    reference's own entropy_model.py produced (tests/golden/make_golden.py), bit for bit in float32 and in torchac's uint16
+    conversion -- the precondition for _F.bin being decodable on either side."""
+    from oracle import entropy_ref, rangecoder_ref
+    from pcgcv2_b200.entropy_host import HostTable
+    from util import load_ckpt
+    gold = np.load(os.path.join(GOLDEN, f"entropy_{name}.npz"))
+    p = entropy_ref.params_from_state_dict(load_ckpt(name))
+    host = HostTable(p["matrices"], p["biases"], p["factors"])
+    checked = 0
+    for key in gold.files:
+        if not key.startswith("cdf_"):
+            continue
+        _, lo, hi = key.split("_")
+        cdf = host.cdf_float(int(lo), int(hi))
+        assert cdf.dtype == np.float32 and np.array_equal(cdf, gold[key]), key
+        lp = cdf.shape[1]
+        u16 = (np.round(cdf * np.float32(65536 - (lp - 1))).astype(np.int64) + np.arange(lp)).astype(np.uint16)
+        assert np.array_equal(u16, rangecoder_ref.cdf_float_to_u16(gold[key]).astype(np.uint16)), key
+        checked += 1
+    assert checked >= 1
+
+
+def test_range_coder_from_symbol_intervals_is_the_same_stream():
+    """pcgc_rc_encode_ranges_host (intervals as pcgc_symbol_ranges writes them) == the table-walking coder == the oracle."""
+    from oracle import rangecoder_ref
+    rng = np.random.default_rng(5)
+    C, L = 8, 19
+    pmf = rng.random((C, L)) ** 4 + 1e-9
+    pmf /= pmf.sum(1, keepdims=True)
+    cdf = np.concatenate([np.zeros((C, 1)), np.cumsum(pmf, 1)], 1).clip(max=1).astype(np.float32)
+    tab = rangecoder_ref.cdf_float_to_u16(cdf).astype(np.uint16)
+    sym = rng.integers(0, L, size=(3000, C)).astype(np.int16)
+    sym[:40] = L - 1                                                       # the last symbol: c_high = 0x10000
+    flat, rows = sym.reshape(-1), np.arange(sym.size) % C
+    lo = tab[rows, flat].astype(np.uint32)
+    hi = np.where(flat == L - 1, 65536, tab[rows, np.minimum(flat + 1, L)]).astype(np.uint32)
+    got = ops.rc_encode_ranges(lo | ((hi - 1) << 16))
+    assert got == ops.rc_encode_u16(tab, sym) == rangecoder_ref.encode_u16(tab, rows.astype(np.int32), flat)
+    assert ops.rc_encode_ranges(np.zeros(0, np.uint32)) == ops.rc_encode_u16(tab, np.zeros((0, C), np.int16))

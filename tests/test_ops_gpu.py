@@ -747,3 +747,26 @@ def test_eb_quantize_symbols():
     ref_sym, ref_lo, ref_hi = entropy_ref.quantize_symbols(f)
     assert (lo, hi) == (int(ref_lo), int(ref_hi))
     assert torch.equal(sym.cpu(), ref_sym)
+
+
+def test_symbol_ranges_on_the_device_code_the_same_stream():
+    """section 8b pcgc_symbol_ranges: per-symbol (c_low, c_high) looked up on the GPU == the host coder's table walk; the
+    stream coded from them is byte-identical (and == the oracle's); a symbol outside the alphabet raises."""
+    gold = np.load(os.path.join(GOLDEN, "entropy_r3.npz"))
+    key = [k for k in gold.files if k.startswith("cdf_")][0]
+    tab = rangecoder_ref.cdf_float_to_u16(gold[key]).astype(np.uint16)
+    C, lp = tab.shape
+    rng = np.random.default_rng(9)
+    sym = rng.integers(0, lp - 1, size=(13784, C)).astype(np.int16)
+    ranges = ops.symbol_ranges(torch.from_numpy(sym).to(DEV), torch.from_numpy(tab.view(np.int16)).to(DEV)).cpu().numpy()
+    flat, rows = sym.reshape(-1), np.arange(sym.size) % C
+    lo = tab[rows, flat].astype(np.uint32)
+    hi = np.where(flat == lp - 2, 65536, tab[rows, np.minimum(flat + 1, lp - 1)]).astype(np.uint32)
+    assert np.array_equal(ranges.view(np.uint32), lo | ((hi - 1) << 16))
+    stream = ops.rc_encode_ranges(ranges)
+    assert stream == ops.rc_encode_u16(tab, sym) == rangecoder_ref.encode_u16(tab, rows.astype(np.int32), flat)
+    assert np.array_equal(ops.rc_decode_u16(tab, stream, sym.size), flat)
+    bad = sym.copy()
+    bad[7, 3] = lp - 1
+    with pytest.raises(ValueError):
+        ops.symbol_ranges(torch.from_numpy(bad).to(DEV), torch.from_numpy(tab.view(np.int16)).to(DEV))
