@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = ``--depth`` (default 2) point-cloud frames per GPU, each through one full ``Codec.encode`` +
+One "step" = ``--depth`` (default 4) point-cloud frames per GPU, each through one full ``Codec.encode`` +
 ``Codec.decode`` (BASELINE.json config 2 stand-in: ``synthetic_vox10``, 795 124 occupied voxels, r3
 checkpoint, rho = 1), kept in flight together by ``pcgcv2_b200.pipeline.FramePipeline`` (one host thread +
 CUDA stream per frame, so the sequential host range coder of one frame overlaps the kernels of the
@@ -329,13 +329,13 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"bound": "hbm", **dom, "peak": hbm_peak, "peak_source": peak_src,
                      "timed_in": f"{args.steps} one-frame-at-a-time steps inside bench.py (CUDA events on the launching stream); "
-                                 "with 2 frames in flight the events also cover kernels of the other stream sharing the SMs",
+                                 f"with {depth} frames in flight the events also cover kernels of the other streams sharing the SMs",
                      "traffic": ncu_traffic_bytes(),
                      "wide_layer": wide,
                      "whole_pass": {"algorithmic_bytes_convs": alg_convs, "algorithmic_bytes_all": alg_all,
                                     "frame_ms_pipelined": round(frame_ms, 3),
                                     "frac": round(alg_convs / (frame_ms * 1e-3) / 1e9 / hbm_peak, 4),
-                                    "note": "106 convolutions' SURVEY 8(d) bytes / wall time per frame with 2 frames in flight (upper bound on "
+                                    "note": f"106 convolutions' SURVEY 8(d) bytes / wall time per frame with {depth} frames in flight (upper bound on "
                                             "GPU-busy time) / HBM peak"}},
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -420,7 +420,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=2, help="frames in flight per GPU (1 = one frame at a time)")
+    ap.add_argument("--depth", type=int, default=4,
+                    help="frames in flight per GPU (1 = one frame at a time; measured on B200: 2 -> 96, 3 -> 108, 4 -> 112, 6 -> 115 "
+                         "Mpoints/s, profiles/r02_depth_sweep.txt)")
     ap.add_argument("--workload", default="codec", choices=["codec", "train"],
                     help="codec = BASELINE's headline (default); train = the config-5 training step (tools/bench_train.py)")
     ap.add_argument("--batch", type=int, default=32, help="--workload train: samples per rank and step")

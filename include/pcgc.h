@@ -43,6 +43,8 @@ extern "C" {
 
 /* epilogue flags of the convolution entry points */
 #define PCGC_EPI_RELU 1       /* out = max(out, 0) after bias (+ residual) */
+#define PCGC_TILES_CHUNKED 256 /* full-octet kernels: every CTA walks one contiguous run of tiles (L1 reuse of shared halo faces)
+                                * instead of the strided order; set by the library itself (PCGC_OCTET_TILE_ORDER=0 disables) */
 
 int pcgc_version(void);
 const char *pcgc_last_error(void);

@@ -57,6 +57,16 @@ struct OctetH2Tune {
     static constexpr int WARPS = DB ? (V == 1 ? 10 : 8) : (NT ? 8 : (COUT == 16 ? 8 : 16));
 };
 
+// PCGC_OCTET_TILE_ORDER=0 keeps the strided tile order; default 1 = one contiguous run of tiles per CTA
+static int octet_tile_flag() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PCGC_OCTET_TILE_ORDER");
+        v = (e && atoi(e) == 0) ? 0 : PCGC_TILES_CHUNKED;
+    }
+    return v;
+}
+
 static int octet_h2_variant() {
     static int v = -1;
     if (v < 0) {
@@ -85,7 +95,7 @@ static int launch_octet_h2_v(const uint32_t *in, int in_ld, const int32_t *pnbr,
     }
     kern<<<grid_for(n_par, C::OCTETS_PER_CTA, ctas), C::THREADS, C::smem_bytes(), s>>>(in, in_ld, pnbr, n_par, packed, inv_scale, bias,
                                                                                      res, res_ld, out, out_ld, out_h2, out_h2_ld,
-                                                                                     flags, overflow);
+                                                                                     flags | octet_tile_flag(), overflow);
     return check_launch("conv_k3_octet_h2");
 }
 
@@ -117,7 +127,7 @@ static int launch_octet_h2c4(const uint32_t *in, int in_ld, const int32_t *pnbr,
     }
     kern<<<grid_for(n_par, C::OCTETS_PER_CTA, ctas), C::THREADS, C::smem_bytes(), s>>>(in, in_ld, pnbr, n_par, packed, inv_scale, bias,
                                                                                      res, res_ld, out, out_ld, out_h2, out_h2_ld,
-                                                                                     flags, overflow);
+                                                                                     flags | octet_tile_flag(), overflow);
     return check_launch("conv_k3_octet_h2c4");
 }
 

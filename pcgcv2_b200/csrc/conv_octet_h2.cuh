@@ -77,31 +77,41 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
     const uint32_t ldb = (uint32_t)in_ld * 4u;
     H2Epilogue epi{bias, residual, out, out_h2, res_ld, out_ld, out_h2_ld, flags, inv_scale};
     int32_t prow[OW];                                               // parent rows of the next tile to stage (lane k: neighbour k)
+#ifndef PCGC_KNOCKOUT                                               // tuning builds only (tools/knockout.sh): drop one phase, time the rest
+#define PCGC_KNOCKOUT 0
+#endif
+    constexpr bool ko_fill = PCGC_KNOCKOUT & 1, ko_xlds = PCGC_KNOCKOUT & 2, ko_wlds = PCGC_KNOCKOUT & 4, ko_mma = PCGC_KNOCKOUT & 8;
     auto stage = [&](unsigned char *buf) {                          // rows -> this buffer's index slice -> cp.async of the halos
         int32_t *sidx = reinterpret_cast<int32_t *>(buf + (size_t)OW * HB);
         store_parent_rows<OW>(sidx, prow, lane);
         __syncwarp();
-        halo_fill<PPR, OW, HB, ROWB, SY, SZ, (KS >= 2)>(buf, sidx, in_bytes, ldb, lane);
+        if constexpr (!ko_fill) halo_fill<PPR, OW, HB, ROWB, SY, SZ, (KS >= 2)>(buf, sidx, in_bytes, ldb, lane);
     };
-    load_parent_rows<OW>(prow, pnbr, n_par, (int64_t)blockIdx.x * C::OCTETS_PER_CTA + warp * OW, lane);
+    // tile order: strided (tile = blockIdx.x + i * gridDim.x) or, with PCGC_TILES_CHUNKED in `flags`, one contiguous run of
+    // tiles per CTA: Morton-consecutive tiles share a face of their halos, which then still sits in this SM's L1
+    const bool chunked = flags & PCGC_TILES_CHUNKED;
+    const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t tile_begin = chunked ? blockIdx.x * per_cta : blockIdx.x, tile_step = chunked ? 1 : gridDim.x;
+    const int64_t tile_end = chunked ? min(n_tiles, tile_begin + per_cta) : n_tiles;
+    load_parent_rows<OW>(prow, pnbr, n_par, tile_begin * C::OCTETS_PER_CTA + warp * OW, lane);
     int cur = 0;
     if constexpr (DB) {                                             // prologue: the first tile's halos
         stage(halo0);
-        load_parent_rows<OW>(prow, pnbr, n_par, ((int64_t)blockIdx.x + gridDim.x) * C::OCTETS_PER_CTA + warp * OW, lane);
+        load_parent_rows<OW>(prow, pnbr, n_par, (tile_begin + tile_step) * C::OCTETS_PER_CTA + warp * OW, lane);
     }
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = tile_begin; tile < tile_end; tile += tile_step) {
         const int64_t oct0 = tile * C::OCTETS_PER_CTA + warp * OW;                // first octet of this warp
         __syncwarp();                                                             // previous iteration's readers are done
         unsigned char *halo;
         if constexpr (DB) {                // stage tile + gridDim.x into the other buffer: its loads fly during this tile's MMAs
             halo = halo0 + (size_t)cur * C::buf_bytes();
             stage(halo0 + (size_t)(cur ^ 1) * C::buf_bytes());                    // (past the end: rows are -1, zero fill, no traffic)
-            load_parent_rows<OW>(prow, pnbr, n_par, (tile + 2 * (int64_t)gridDim.x) * C::OCTETS_PER_CTA + warp * OW, lane);
+            load_parent_rows<OW>(prow, pnbr, n_par, (tile + 2 * tile_step) * C::OCTETS_PER_CTA + warp * OW, lane);
             cur ^= 1;
         } else {
             halo = halo0;
             stage(halo0);
-            load_parent_rows<OW>(prow, pnbr, n_par, (tile + gridDim.x) * C::OCTETS_PER_CTA + warp * OW, lane);
+            load_parent_rows<OW>(prow, pnbr, n_par, (tile + tile_step) * C::OCTETS_PER_CTA + warp * OW, lane);
         }
 
         float acc[CT][RG][4], small[CT][RG][4];
@@ -127,8 +137,8 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
 #pragma unroll
         for (int o = 0; o < 27; ++o) {
             if ((o + 1) % 9 == 0 && o + 1 < 27) halo_wait_db<DB ? 4 : 0>((o + 1) / 9);   // next z-plane of the halo
-            if (o + 1 < 27) load_frags(o + 1, xb[(o + 1) & 1]);
-            uint4 (&x)[NR][KS] = xb[o & 1];
+            if (o + 1 < 27 && !ko_xlds) load_frags(o + 1, xb[(o + 1) & 1]);
+            uint4 (&x)[NR][KS] = xb[ko_xlds ? 0 : (o & 1)];                       // (ko_xlds is a compile-time constant)
             const uint32_t *wb = wsm + (size_t)o * W_OFF;
             float part[CT][RG][4];
 #pragma unroll
@@ -157,8 +167,16 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
                 } else {
 #pragma unroll
                     for (int c = 0; c < CT; ++c) {
-                        const uint4 *wp = reinterpret_cast<const uint4 *>(wb + (q * CT + c) * 256) + lane;
+                        const uint4 *wp = reinterpret_cast<const uint4 *>((ko_wlds ? wsm : wb) + (q * CT + c) * 256) + lane;
                         const uint4 wh = wp[0], wl = wp[32];
+                        if constexpr (ko_mma) {
+#pragma unroll
+                            for (int r = 0; r < RG; ++r) {
+                                part[c][r][0] = __uint_as_float(wh.x ^ x[r][q].x); part[c][r][1] = __uint_as_float(wh.y ^ x[r][q].y);
+                                part[c][r][2] = __uint_as_float(wl.z ^ x[r][q].z); part[c][r][3] = __uint_as_float(wl.w ^ x[r][q].w);
+                            }
+                            continue;
+                        }
 #pragma unroll
                         for (int r = 0; r < RG; ++r) mma_f16(small[c][r], wh.x, wh.y, wh.z, wh.w, x[r][q].z, x[r][q].w);      // W_hi * X_lo
 #pragma unroll
@@ -287,14 +305,18 @@ conv_k3_octet_h2c4_kernel(const uint32_t *__restrict__ in, int in_ld, const int3
     const uint32_t ldb = (uint32_t)in_ld * 4u;
     H2Epilogue epi{bias, residual, out, out_h2, res_ld, out_ld, out_h2_ld, flags, inv_scale};
     int32_t prow[OW];
-    load_parent_rows<OW>(prow, pnbr, n_par, (int64_t)blockIdx.x * C::OCTETS_PER_CTA + warp * OW, lane);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const bool chunked = flags & PCGC_TILES_CHUNKED;                // see conv_k3_octet_h2_kernel
+    const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t tile_begin = chunked ? blockIdx.x * per_cta : blockIdx.x, tile_step = chunked ? 1 : gridDim.x;
+    const int64_t tile_end = chunked ? min(n_tiles, tile_begin + per_cta) : n_tiles;
+    load_parent_rows<OW>(prow, pnbr, n_par, tile_begin * C::OCTETS_PER_CTA + warp * OW, lane);
+    for (int64_t tile = tile_begin; tile < tile_end; tile += tile_step) {
         const int64_t oct0 = tile * C::OCTETS_PER_CTA + warp * OW;
         __syncwarp();
         store_parent_rows<OW>(sidx, prow, lane);
         __syncwarp();
         halo_fill<1, OW, HB, 16, SY, SZ, false>(halo, sidx, in_bytes, ldb, lane);
-        load_parent_rows<OW>(prow, pnbr, n_par, (tile + gridDim.x) * C::OCTETS_PER_CTA + warp * OW, lane);
+        load_parent_rows<OW>(prow, pnbr, n_par, (tile + tile_step) * C::OCTETS_PER_CTA + warp * OW, lane);
 
         float acc[CT][RG][4];
 #pragma unroll
