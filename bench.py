@@ -199,7 +199,7 @@ def run_ours(args, rank, world, local_rank):
     n0 = len(pts)
     depth = max(1, args.depth)
     sd = load_weights("r3")
-    pipe = FramePipeline(sd, device=dev, depth=depth)          # `depth` frames in flight on this GPU
+    pipe = FramePipeline(sd, device=dev, depth=depth, coord_bits=10)   # `depth` frames in flight on this GPU; vox10: --res 1024
     codec = pipe.codecs[0]
     host_coords = torch.from_numpy(pts).pin_memory()
     dev_coords = host_coords.to(dev)
@@ -315,6 +315,8 @@ def run_ours(args, rank, world, local_rank):
                    "bpp_coords": round(int(counters[:, 4].sum()) / total_pts, 5),
                    "coords_side_channel": "in-process octree coder (own format, ~1.5 bits per bottleneck point; tmc3 gives ~1.0: parity runs "
                                           "use Tmc3CoordinateCoder), coded and decoded inside every timed frame on a side thread",
+                   "coord_bits": "10 (the --res=1024 of coder.py:196 handed to Codec: radix sorts run over 30 key bits; inputs beyond it are "
+                                 "detected on the device and re-coded at full width)",
                    "cdf_table": "built on the host once per symbol range and cached: after warm-up no table work is left in the timed region",
                    "per_rank": {"ms_per_step": [round(v / 1e3, 3) for v in counters[:, 5].tolist()],
                                 "e2e_ms_per_step": [round(v / 1e3, 3) for v in counters[:, 6].tolist()],

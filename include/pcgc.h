@@ -62,8 +62,11 @@ int pcgc_pack_keys(const int32_t *coords, int64_t n, int32_t tensor_stride, uint
                    int32_t *err_flag, void *stream);
 
 /* the same from int32 [n,3] = (x,y,z) rows with one batch index for all rows (coder.py is
- * batch-1 by construction, coder.py:97,106): no padded [n,4] copy of the cloud is needed. */
-int pcgc_pack_keys3(const int32_t *coords3, int64_t n, int32_t tensor_stride, int32_t batch, uint64_t *keys,
+ * batch-1 by construction, coder.py:97,106): no padded [n,4] copy of the cloud is needed.
+ * hint_bits > 0: the caller expects every coordinate / stride below 2^hint_bits and batch 0 (the --res of coder.py:196) and
+ * will sort only the low 3 * hint_bits key bits; bit 1 of *err_flag is raised when a row breaks the hint (the caller then
+ * repeats with the full key width), bit 0 as above. */
+int pcgc_pack_keys3(const int32_t *coords3, int64_t n, int32_t tensor_stride, int32_t batch, int32_t hint_bits, uint64_t *keys,
                     int32_t *err_flag, void *stream);
 
 /* a5  gather map of ME.MinkowskiConvolution(k=2, s=2) -- autoencoder.py:78,97,116: child_map
@@ -267,10 +270,14 @@ int pcgc_convT_k2s2_fwd_h2out(const float *in, int32_t in_ld, int64_t n_in, cons
  * the caller does not want the h2 copy.  ws: pcgc_irn_ws_bytes(n, c) bytes of device memory for the temporaries. */
 enum { PCGC_ROUTE_H2_GATHER = 0, PCGC_ROUTE_H2_OCTET = 1, PCGC_ROUTE_TF32_GATHER = 2, PCGC_ROUTE_TF32_OCTET = 3, PCGC_ROUTE_FP32 = 4,
        PCGC_ROUTE_WIDE = 5 /* tcgen05 / TMA kernel (pcgc_conv_k3_wide_fwd): h2 features, child map */ };
+/* PCGC_IRN_MERGED_FIRST: w3[0] / b3[0] / inv_scale[0] describe ONE k=3 convolution c -> c/2 that computes conv0_0 (output
+ * channels 0..c/4-1) and conv1_0 (channels c/4..c/2-1: its k=1 weights at the centre offset 13, zeros elsewhere) -- both read x
+ * and both are followed by a ReLU (autoencoder.py:52-57); w1[0] / b1[0] are ignored.  All three routes must be h2 routes. */
+#define PCGC_IRN_MERGED_FIRST 1
 typedef struct pcgc_irn_args {
     int64_t n;                      /* rows of the coordinate set */
     int32_t c;                      /* block channels (16, 32, 64) */
-    int32_t reserved;
+    int32_t reserved;               /* flags: PCGC_IRN_MERGED_FIRST */
     const int32_t *nbr;             /* [27][n] kernel map of the set (gather routes), or NULL */
     const int32_t *parent_nbr;      /* [27][n/8] kernel map of the parent set (octet routes), or NULL */
     const float *x;                 /* block input fp32, leading dimension x_ld */

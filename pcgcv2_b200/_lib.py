@@ -34,7 +34,7 @@ SIGNATURES = {
     "pcgc_last_error": (ctypes.c_char_p, []),
     "pcgc_launch_count": (ctypes.c_uint64, []),
     "pcgc_pack_keys": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p]),
-    "pcgc_pack_keys3": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_p, c_p, c_p]),
+    "pcgc_pack_keys3": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p]),
     "pcgc_child_map_k2": (ctypes.c_int, [c_p, c_p, c_i64, c_i64, c_p, c_p]),
     "pcgc_scale_coords": (ctypes.c_int, [c_p, c_i64, ctypes.c_float, c_p, c_p]),
     "pcgc_unpack_keys": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p]),

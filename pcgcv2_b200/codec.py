@@ -96,9 +96,15 @@ class Codec:
     WIDE_SHAPES = {(64, 64)}            # (cin, cout) of the k=3 layers routed to the tcgen05 / TMA kernel
 
     def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True, use_h2=True, fuse_irn=True,
-                 coords_coder="octree", wide_shapes=None):
+                 coords_coder="octree", wide_shapes=None, merge_first=True, coord_bits=None):
         """``coords_coder``: "octree" (in-process, default), None (hand the coordinates over raw, no ``Stream.C``) or any
         object with ``encode(int32 [n,3]) -> bytes`` / ``decode(bytes) -> int32 [n,3]`` (e.g. ``Tmc3CoordinateCoder``)."""
+        # ``coord_bits``: the caller's promise that every input coordinate is below 2^coord_bits (coder.py's --res: 10 for vox10).
+        # The radix sorts then run over 3 * coord_bits key bits instead of 57; an input that breaks the promise raises a device
+        # flag that is read with the pass's synchronising read, and the frame is coded again at full width (coord_bits_fallbacks).
+        self.coord_bits = None if coord_bits is None else max(4, min(19, int(coord_bits)))
+        self.coord_bits_fallbacks = 0
+        self.merge_first = merge_first      # conv0_0 + conv1_0 of the 16-channel blocks as one k=3 convolution (see _merged_first)
         self.coords_coder = OctreeCoordinateCoder() if coords_coder == "octree" else coords_coder
         self._side = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pcgc-coords") if self.coords_coder is not None else None
         self.device = torch.device(device)
@@ -174,6 +180,7 @@ class Codec:
                     if pw.packed is not None:
                         (self.packed_down_h2 if ".down" in name else self.packed_up_h2)[name] = pw
         self._h2_on = bool(self.packed_h2)
+        self._merged = {}
         self.use_octet = use_octet_kernels
         self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)   # raised by an h2 producer: re-run in fp32
         self._bad = torch.zeros(1, dtype=torch.int32, device=self.device)        # raised by pack_keys: coordinate out of range
@@ -303,6 +310,25 @@ class Codec:
             return _lib.ROUTE_TF32_GATHER, pw.packed, 1.0
         return _lib.ROUTE_FP32, self.w[name + ".kernel"], 1.0
 
+    def _merged_first(self, prefix):
+        """conv0_0 (k=3, c -> c/4) and conv1_0 (k=1, c -> c/4) of one InceptionResNet block as ONE k=3 convolution c -> c/2:
+        output channels c/4.. carry conv1_0's weights at the centre offset.  Worth it where the 8-wide MMA tile of conv0_0 is
+        half empty (c = 16): -> (packed h2 weights, bias [1, c/2]) or None."""
+        m = self._merged.get(prefix)
+        if m is None:
+            w0, w1 = self.w[prefix + ".conv0_0.kernel"], self.w[prefix + ".conv1_0.kernel"]
+            c, q = int(w0.shape[1]), int(w0.shape[2])
+            m = False
+            if self.merge_first and c == 16 and w1.shape == (c, q) and ops.octet_h2_supported(c, 2 * q):
+                wm = torch.zeros((27, c, 2 * q), dtype=torch.float32, device=self.device)
+                wm[:, :, :q] = w0
+                wm[13, :, q:] = w1                                    # k = ix + 3 iy + 9 iz with i = 1: the centre offset
+                bias = torch.cat([self.w[prefix + ".conv0_0.bias"], self.w[prefix + ".conv1_0.bias"]], dim=1).contiguous()
+                pk = ops.PackedK3H2(wm.contiguous())
+                m = (pk, bias) if pk.packed is not None else False
+            self._merged[prefix] = m
+        return m or None
+
     def _irn_plan(self, prefix, full_octets):
         key = (prefix, full_octets, self._h2_on)
         plan = self._irn_plans.get(key)
@@ -314,6 +340,15 @@ class Codec:
                 args.route[i], args.inv_scale[i] = route, inv
                 args.w3[i], args.b3[i] = w.data_ptr(), self.w[prefix + leaf + ".bias"].data_ptr()
                 keep.append(w)
+            h2_routes = (_lib.ROUTE_H2_GATHER, _lib.ROUTE_H2_OCTET, _lib.ROUTE_WIDE)
+            merged = self._merged_first(prefix) if (self._h2_on and full_octets and self.use_octet and
+                                                    all(r in h2_routes for r in args.route)) else None
+            if merged is not None:
+                pk, bias = merged
+                args.reserved = 1                                     # PCGC_IRN_MERGED_FIRST
+                args.route[0], args.inv_scale[0] = _lib.ROUTE_H2_OCTET, pk.inv_scale
+                args.w3[0], args.b3[0] = pk.packed.data_ptr(), bias.data_ptr()
+                keep += [pk.packed, bias]
             for i, leaf in enumerate((".conv1_0", ".conv1_2")):
                 args.w1[i], args.b1[i] = self.w[prefix + leaf + ".kernel"].data_ptr(), self.w[prefix + leaf + ".bias"].data_ptr()
             routes = list(args.route)
@@ -384,8 +419,9 @@ class Codec:
         """int32 [N,4] on the device -> (level-0 coordinate set in Morton order, device flag "has duplicates").
         Duplicates are rare: the first pass only raises the flag (read together with the symbol range, no extra
         synchronisation); ``dedupe`` drops them (``unique_consecutive`` synchronises for the output size)."""
-        keys = ops.pack_keys_async(coords, 1, self._bad)             # range flag: read with the pass's synchronising read
-        keys, _ = ops.argsort_u64(keys)
+        bits = self.coord_bits if (self.coord_bits is not None and coords.shape[1] == 3) else 0
+        keys = ops.pack_keys_async(coords, 1, self._bad, hint_bits=bits)   # range flags: read with the pass's synchronising read
+        keys, _ = ops.argsort_u64(keys, end_bit=3 * bits if bits else 64)
         if dedupe:
             keys = torch.unique_consecutive(keys)
         dup = (keys[1:] == keys[:-1]).any().to(torch.int32).reshape(1) if keys.numel() > 1 else self._overflow.new_zeros(1)
@@ -460,12 +496,13 @@ class Codec:
 
     # ---------------------------------------------------------------- codec
     @staticmethod
-    def _canonical_order(coords3: torch.Tensor) -> torch.Tensor:
+    def _canonical_order(coords3: torch.Tensor, bits: int = 20) -> torch.Tensor:
         """argsort of the reference's sort key b + x*S + y*S^2 + z*S^3 (data_utils.py:55-61,91-101):
-        z most significant, x least -- any S > max gives the same order."""
+        z most significant, x least -- any S > max gives the same order.  ``bits``: every coordinate is below 2^bits (the
+        radix sort then runs over 3 * bits key bits)."""
         c = coords3.long()
-        key = (c[:, 2] << 40) | (c[:, 1] << 20) | c[:, 0]
-        return ops.argsort_u64(key.contiguous(), end_bit=60)[1].long()
+        key = (c[:, 2] << (2 * bits)) | (c[:, 1] << bits) | c[:, 0]
+        return ops.argsort_u64(key.contiguous(), end_bit=3 * bits)[1].long()
 
     def _h2_overflowed(self) -> bool:
         """True when an h2 producer met a value outside the f16 range during the pass that just finished (call
@@ -495,8 +532,12 @@ class Codec:
     def encode(self, coords) -> Stream:
         """coords: int32 [N,3] (or [N,4] with the batch column; batch 0 only) host array or tensor."""
         st = self._encode(coords)
-        while not isinstance(st, Stream):                                # "dup": duplicates in the input; "h2": f16 range left
-            st = self._encode(coords, dedupe=True) if st == "dup" else self._without_h2(self._encode, coords, self._dedupe_next)
+        while not isinstance(st, Stream):                                # "dup": duplicates in the input; "h2": f16 range left;
+            if st == "bits":                                             # "bits": a coordinate above the coord_bits promise
+                self.coord_bits, self.coord_bits_fallbacks = None, self.coord_bits_fallbacks + 1
+                st = self._encode(coords)
+            else:
+                st = self._encode(coords, dedupe=True) if st == "dup" else self._without_h2(self._encode, coords, self._dedupe_next)
         return st
 
     def decode(self, stream: Stream, rho: float = 1.0, to_host: bool = True):
@@ -543,7 +584,7 @@ class Codec:
         level0, dup = self._sorted_input(coords, dedupe)
         y, level3, num_points = self.analysis(level0)
         c3 = ops.unpack_keys(level3.keys, 1)[:, 1:]                       # stride-8 coordinates / 8
-        order = self._canonical_order(c3)
+        order = self._canonical_order(c3, max(1, self.coord_bits - 3) if self.coord_bits is not None else 20)   # c3 = coordinates / 8
         y, c3 = y[order].contiguous(), c3[order].contiguous()
         sym, mm = ops.eb_quantize_async(y)
         # one synchronising read for everything the host needs: symbol range + flags, symbols, coordinates
@@ -554,10 +595,14 @@ class Codec:
         c3_h.copy_(c3, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         lo, hi, over, has_dup, bad = flags_h.tolist()
-        if bad:
+        if bad & 1:
             self._bad.zero_()
             self._overflow.zero_()
             raise ValueError("coordinates out of range: need 0 <= c <= %d, batch <= 126" % ((1 << 19) - 1))
+        if bad & 2:                                                       # a coordinate above the coord_bits promise: the sorts were too
+            self._bad.zero_()                                             # narrow; code the frame again at full key width
+            self._overflow.zero_()
+            return "bits"
         if has_dup:
             if over:
                 self._overflow.zero_()                                    # the deduplicated re-run decides for itself
@@ -595,12 +640,14 @@ class Codec:
         c3_h = self._staging("c3_in", (n3, 3), torch.int32)
         c3_h.copy_(torch.as_tensor(coords_in, dtype=torch.int32))
         c3 = c3_h.to(self.device, non_blocking=True)
-        c3 = c3[self._canonical_order(c3)]                               # coder.py:97-99 (runs while the host decodes the symbols)
+        cmax = int(c3_h.max()) if n3 else 0                               # host data: the exact key width of the two small sorts
+        cbits = max(1, cmax.bit_length()) if 0 <= cmax < (1 << 19) and (n3 == 0 or int(c3_h.min()) >= 0) else 0
+        c3 = c3[self._canonical_order(c3, cbits or 20)]                  # coder.py:97-99 (runs while the host decodes the symbols)
         keys = ops.pack_keys_async(c3, 1, self._bad)                      # = the stride-8 keys of 8 * c3 (keys hold coordinate / stride)
         if stream.C is None:
             ops.rc_decode_u16(self._host_table(lo, hi), stream.F, n3 * ch, out=sym_h.numpy().reshape(-1))
         y = sym_h.to(self.device, non_blocking=True).float() + float(lo)
-        keys, order = ops.argsort_u64(keys)                              # Morton order for the synthesis network
+        keys, order = ops.argsort_u64(keys, end_bit=3 * cbits if cbits else 64)   # Morton order for the synthesis network
         level3 = _Level(keys, 8)
         nums = np.frombuffer(stream.num_points, dtype=np.int32).tolist()
         nums[-1] = int(rho * nums[-1])                                   # coder.py:107

@@ -25,7 +25,7 @@ __global__ void pack_keys_kernel(const int4 *__restrict__ coords, int64_t n, int
 }
 
 // the same from int32 [n,3] (x, y, z) rows with one batch index for all (Codec's input: no padded copy of the cloud)
-__global__ void pack_keys3_kernel(const int32_t *__restrict__ coords, int64_t n, int32_t stride, int32_t batch,
+__global__ void pack_keys3_kernel(const int32_t *__restrict__ coords, int64_t n, int32_t stride, int32_t batch, int32_t hint_bits,
                                   uint64_t *__restrict__ keys, int32_t *__restrict__ err) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int cx = coords[3 * i], cy = coords[3 * i + 1], cz = coords[3 * i + 2];
@@ -36,6 +36,7 @@ __global__ void pack_keys3_kernel(const int32_t *__restrict__ coords, int64_t n,
             *err = 1;
             keys[i] = 0;
         } else {
+            if (hint_bits > 0 && ((((uint32_t)x | (uint32_t)y | (uint32_t)z) >> hint_bits) != 0u || batch != 0)) atomicOr(err, 2);
             keys[i] = make_key((uint32_t)batch, (uint32_t)x, (uint32_t)y, (uint32_t)z);
         }
     }
@@ -252,11 +253,12 @@ int pcgc_pack_keys(const int32_t *coords, int64_t n, int32_t tensor_stride, uint
     return check_launch("pack_keys");
 }
 
-int pcgc_pack_keys3(const int32_t *coords3, int64_t n, int32_t tensor_stride, int32_t batch, uint64_t *keys, int32_t *err_flag,
-                    void *stream) {
-    PCGC_REQUIRE(n >= 0 && tensor_stride >= 1 && batch >= 0 && batch <= PCGC_MAX_BATCH, "pcgc_pack_keys3: bad arguments");
+int pcgc_pack_keys3(const int32_t *coords3, int64_t n, int32_t tensor_stride, int32_t batch, int32_t hint_bits, uint64_t *keys,
+                    int32_t *err_flag, void *stream) {
+    PCGC_REQUIRE(n >= 0 && tensor_stride >= 1 && batch >= 0 && batch <= PCGC_MAX_BATCH && hint_bits >= 0 && hint_bits <= 19,
+                 "pcgc_pack_keys3: bad arguments");
     if (n == 0) return PCGC_OK;
-    pack_keys3_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(coords3, n, tensor_stride, batch, keys, err_flag);
+    pack_keys3_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(coords3, n, tensor_stride, batch, hint_bits, keys, err_flag);
     return check_launch("pack_keys3");
 }
 

@@ -69,7 +69,8 @@ int pcgc_irn_fwd(const pcgc_irn_args *a, void *stream) {
             return PCGC_ERR_INVALID;
         }
     }
-    if (!a->x || !a->out || !a->ws || a->ws_bytes < pcgc_irn_ws_bytes(a->n, c) || !a->w1[0] || !a->w1[1]) {
+    if (!a->x || !a->out || !a->ws || a->ws_bytes < pcgc_irn_ws_bytes(a->n, c) || (!a->w1[0] && !(a->reserved & PCGC_IRN_MERGED_FIRST)) ||
+        !a->w1[1]) {
         pcgc::set_error("pcgc_irn_fwd: null pointer or workspace too small");
         return PCGC_ERR_INVALID;
     }
@@ -87,9 +88,27 @@ int pcgc_irn_fwd(const pcgc_irn_args *a, void *stream) {
     float *cc_f = (float *)(base + 4 * plane);
     int rc;
 
+    // ---- merged first layers (PCGC_IRN_MERGED_FIRST): conv0_0 and conv1_0 read the same x and are both followed by a ReLU, so
+    // they run as ONE k=3 convolution c -> 2q whose output channels q..2q-1 carry conv1_0's k=1 weights at the centre offset
+    // (zero elsewhere).  With q = 4 the second half of the 8-wide MMA tile was idle anyway: conv1_0 costs nothing, its own
+    // launch and its pass over x disappear.  The h2 result [n][2q] feeds conv0_1 (words 0..q-1) and conv1_1 (words q..2q-1).
+    const bool merged = a->reserved & PCGC_IRN_MERGED_FIRST;
+    if (merged && !(h2_route(a->route[0]) && h2_route(a->route[1]) && h2_route(a->route[2]) && q % 4 == 0)) {
+        pcgc::set_error("pcgc_irn_fwd: merged first layers need h2 routes for all three k=3 layers and c %% 16 == 0");
+        return PCGC_ERR_INVALID;
+    }
+    uint32_t *ab_h = a_h;                                        // merged: [n][2q] over the a_h and b_f planes
+    const int ab_ld = merged ? 2 * q : q;
+    if (merged) {
+        rc = run_k3(a, 0, a->x, a->x_h2, a->x_h2_ld, c, 2 * q, nullptr, 0, nullptr, 0, ab_h, ab_ld, PCGC_EPI_RELU, stream);
+        if (rc) return rc;
+        b_h = ab_h + q;
+    }
+
     // ---- branch 0: conv0_0 (c -> q, ReLU), conv0_1 (q -> h, + x[:, :h])
     const bool a_needs_h2 = h2_route(a->route[1]), a_needs_f32 = !a_needs_h2;
-    if (h2_route(a->route[0]) && q % 4 == 0) {
+    if (merged) {
+    } else if (h2_route(a->route[0]) && q % 4 == 0) {
         rc = run_k3(a, 0, a->x, a->x_h2, a->x_h2_ld, c, q, nullptr, 0, a_needs_f32 ? a_f : nullptr, q, a_needs_h2 ? a_h : nullptr, q,
                     PCGC_EPI_RELU, stream);
         if (rc) return rc;
@@ -103,12 +122,13 @@ int pcgc_irn_fwd(const pcgc_irn_args *a, void *stream) {
         }
     }
     const bool first_half_h2 = want_h2 && h2_route(a->route[1]);
-    rc = run_k3(a, 1, a_f, a_h, q, q, h, a->x, a->x_ld, a->out, a->out_ld, first_half_h2 ? a->out_h2 : nullptr, a->out_h2_ld, 0, stream);
+    rc = run_k3(a, 1, a_f, a_h, ab_ld, q, h, a->x, a->x_ld, a->out, a->out_ld, first_half_h2 ? a->out_h2 : nullptr, a->out_h2_ld, 0, stream);
     if (rc) return rc;
 
     // ---- branch 1: conv1_0 (k=1, c -> q, ReLU), conv1_1 (k=3, q -> q, ReLU), conv1_2 (k=1, q -> h, + x[:, h:])
     const bool b_needs_h2 = h2_route(a->route[2]);
-    if (b_needs_h2 && pcgc_conv_h2out_supported(1, c, q)) {
+    if (merged) {
+    } else if (b_needs_h2 && pcgc_conv_h2out_supported(1, c, q)) {
         rc = pcgc_conv_k1_fwd_h2out(a->x, a->x_ld, a->n, a->w1[0], a->b1[0], c, q, nullptr, 0, b_f, q, b_h, q, PCGC_EPI_RELU, a->overflow, stream);
         if (rc) return rc;
     } else {
@@ -119,7 +139,7 @@ int pcgc_irn_fwd(const pcgc_irn_args *a, void *stream) {
             if (rc) return rc;
         }
     }
-    rc = run_k3(a, 2, b_f, b_h, q, q, q, nullptr, 0, cc_f, q, nullptr, 0, PCGC_EPI_RELU, stream);
+    rc = run_k3(a, 2, b_f, b_h, ab_ld, q, q, nullptr, 0, cc_f, q, nullptr, 0, PCGC_EPI_RELU, stream);
     if (rc) return rc;
     bool second_half_h2 = false;
     if (want_h2 && pcgc_conv_h2out_supported(1, q, h)) {

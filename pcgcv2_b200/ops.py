@@ -72,10 +72,10 @@ def pack_keys(coords: torch.Tensor, tensor_stride: int) -> torch.Tensor:
     return keys
 
 
-def pack_keys_async(coords: torch.Tensor, tensor_stride: int, err: torch.Tensor, batch: int = 0) -> torch.Tensor:
+def pack_keys_async(coords: torch.Tensor, tensor_stride: int, err: torch.Tensor, batch: int = 0, hint_bits: int = 0) -> torch.Tensor:
     """int32 [N,4] (b,x,y,z) or [N,3] (x,y,z; all rows in ``batch``) -> int64 [N] Morton keys WITHOUT reading the range flag
-    back: ``err`` (device int32 [1], zeroed by the caller) is raised on a bad coordinate; the caller reads it with its next
-    synchronising read."""
+    back: ``err`` (device int32 [1], zeroed by the caller) is raised on a bad coordinate (bit 0) or, for [N,3] input with
+    ``hint_bits`` > 0, on a coordinate / stride >= 2^hint_bits (bit 1); the caller reads it with its next synchronising read."""
     _need_cuda(coords)
     if coords.dtype != torch.int32:
         raise ValueError("coordinates must be int32")
@@ -83,7 +83,8 @@ def pack_keys_async(coords: torch.Tensor, tensor_stride: int, err: torch.Tensor,
     n = coords.shape[0]
     keys = torch.empty(n, dtype=torch.int64, device=coords.device)
     if coords.shape[1] == 3:
-        check(_lib.lib().pcgc_pack_keys3(_p(coords), n, int(tensor_stride), int(batch), _p(keys), _p(err), _stream()), "pcgc_pack_keys3")
+        check(_lib.lib().pcgc_pack_keys3(_p(coords), n, int(tensor_stride), int(batch), int(hint_bits), _p(keys), _p(err), _stream()),
+              "pcgc_pack_keys3")
     else:
         check(_lib.lib().pcgc_pack_keys(_p(coords), n, int(tensor_stride), _p(keys), _p(err), _stream()), "pcgc_pack_keys")
     return keys

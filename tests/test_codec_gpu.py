@@ -224,7 +224,7 @@ def test_irn_block_per_c_call_is_the_same_computation(r3, use_h2):
     bit-identical bitstream, bottleneck and decoded set; with and without the h2 kernels; also without octet kernels."""
     pts = synth.ellipsoid_vox8()
     for octet in (True, False):
-        fused = Codec(r3, use_h2=use_h2, use_octet_kernels=octet, fuse_irn=True)
+        fused = Codec(r3, use_h2=use_h2, use_octet_kernels=octet, fuse_irn=True, merge_first=False)
         plain = Codec(r3, use_h2=use_h2, use_octet_kernels=octet, fuse_irn=False)
         a, b = fused.encode(pts), plain.encode(pts)
         assert a.F == b.F and a.H == b.H and (a.coords == b.coords).all() and fused._irn_plans and not plain._irn_plans
@@ -245,3 +245,50 @@ def test_tcgen05_routes_give_the_same_stream_and_occupancy(r3):
     assert every.h2_fallbacks == 0 and default.h2_fallbacks == 0
     plain = Codec(r3, wide_shapes="all", fuse_irn=False)                 # layer-by-layer == one C call per block
     assert plain.encode(pts).F == a.F and (canon(plain.decode(a)) == canon(da)).all()
+
+
+def test_merged_first_layers_of_the_16_channel_blocks(r3):
+    """conv0_0 (k=3) + conv1_0 (k=1) of the finest decoder blocks as ONE k=3 convolution 16 -> 8 (conv1_0's weights at the
+    centre offset, PCGC_IRN_MERGED_FIRST): the block output stays within the h2 tolerance of the layer-by-layer block, the
+    stream is untouched (the analysis network has no 16-channel block) and the decoded set is the same on the KAT cloud."""
+    pts = synth.ellipsoid_vox8()
+    merged, plain = Codec(r3, merge_first=True), Codec(r3, merge_first=False)
+    a, b = merged.encode(pts), plain.encode(pts)
+    assert a.F == b.F and a.H == b.H and (a.coords == b.coords).all()
+    da, db = merged.decode(a), plain.decode(b)
+    assert any(p["args"].reserved == 1 for p in merged._irn_plans.values())
+    assert not any(p["args"].reserved for p in plain._irn_plans.values())
+    assert (canon(da) == canon(db)).all()
+    # one block in isolation on random features over the finest decoder set of the KAT cloud
+    plain.record = {}
+    plain.decode(b)
+    x, keys, stride = plain.record["decoder.conv2"]
+    plain.record = None
+    from pcgcv2_b200.codec import _F, _Level
+    parent = _Level((keys[::8] >> 3).contiguous(), 2 * stride)
+    level = _Level(keys, stride, parent=parent)
+    g = torch.Generator().manual_seed(1)
+    xr = (torch.randn(x.shape, generator=g) * 2).cuda()
+    with torch.no_grad(), ops.stream_scope():
+        ym = merged._irn_fused("decoder.block2.0", _F(xr.clone()), level).f
+        yp = plain._irn_fused("decoder.block2.0", _F(xr.clone()), level).f
+    err = float((ym - yp).abs().max() / yp.abs().max())
+    assert err < 3e-6, err
+
+
+def test_coord_bits_hint_is_the_same_codec_and_falls_back(r3):
+    """Codec(coord_bits=b): radix sorts over 3 b key bits -- identical stream and decoded set; a cloud that breaks the promise
+    is detected by the device flag and coded again at full key width (coord_bits_fallbacks), with the right result."""
+    pts = synth.ellipsoid_vox8()                                          # coordinates < 256
+    full, hinted = Codec(r3), Codec(r3, coord_bits=8)
+    a, b = full.encode(pts), hinted.encode(pts)
+    assert a.F == b.F and a.H == b.H and a.C == b.C and a.num_points == b.num_points and (a.coords == b.coords).all()
+    assert (canon(hinted.decode(b)) == canon(full.decode(a))).all() and hinted.coord_bits_fallbacks == 0
+    narrow = Codec(r3, coord_bits=7)                                      # 2^7 = 128 < the cloud's extent
+    c = narrow.encode(pts)
+    assert narrow.coord_bits_fallbacks == 1 and narrow.coord_bits is None
+    assert c.F == a.F and (c.coords == a.coords).all() and (canon(narrow.decode(c)) == canon(full.decode(a))).all()
+    shifted = pts + np.array([[4096, 0, 0]], dtype=np.int32)              # decode side: key width comes from the stream's coordinates
+    d = hinted.encode(shifted)
+    assert hinted.coord_bits_fallbacks == 1
+    assert (canon(hinted.decode(d)) == canon(full.decode(full.encode(shifted)))).all()
