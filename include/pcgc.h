@@ -274,6 +274,9 @@ enum { PCGC_ROUTE_H2_GATHER = 0, PCGC_ROUTE_H2_OCTET = 1, PCGC_ROUTE_TF32_GATHER
  * channels 0..c/4-1) and conv1_0 (channels c/4..c/2-1: its k=1 weights at the centre offset 13, zeros elsewhere) -- both read x
  * and both are followed by a ReLU (autoencoder.py:52-57); w1[0] / b1[0] are ignored.  All three routes must be h2 routes. */
 #define PCGC_IRN_MERGED_FIRST 1
+/* PCGC_IRN_FUSED_TAIL: conv1_1 (k=3) and conv1_2 (k=1) run as one kernel (pcgc_conv_k3_octet_h2_k1_fwd); route[2] must be
+ * PCGC_ROUTE_H2_OCTET and the shape supported. */
+#define PCGC_IRN_FUSED_TAIL 2
 typedef struct pcgc_irn_args {
     int64_t n;                      /* rows of the coordinate set */
     int32_t c;                      /* block channels (16, 32, 64) */
@@ -428,6 +431,16 @@ int pcgc_conv_k3_octet_tc05_fwd(const uint32_t *feats_h2, int32_t in_ld, const i
                                 const void *packed, float inv_scale, const float *bias, int32_t cin, int32_t cout,
                                 const float *residual, int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2,
                                 int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream);
+
+/* k=3 convolution + ReLU + the k=1 convolution that follows it, in one kernel (conv1_1 -> conv1_2 of an InceptionResNet
+ * block, autoencoder.py:28,42,55): out = relu(conv_k3(in; packed, bias)) @ tail_weight[cmid][cout] + tail_bias + residual.
+ * The intermediate is never written.  Shapes: pcgc_conv_k3_octet_h2_k1_supported (4 -> 4 -> 8 today); arguments otherwise
+ * as pcgc_conv_k3_octet_h2_fwd. */
+int pcgc_conv_k3_octet_h2_k1_supported(int32_t cin, int32_t cmid, int32_t cout);
+int pcgc_conv_k3_octet_h2_k1_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *parent_nbr, int64_t n_parents,
+                                 const uint32_t *packed, float inv_scale, const float *bias, int32_t cin, int32_t cmid,
+                                 const float *tail_weight, const float *tail_bias, int32_t cout, const float *residual, int32_t res_ld,
+                                 float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t *overflow, void *stream);
 
 /* ---- occupancy loss of the training path (row f4) ----------------------------------------------
  * get_bce(data, ground_truth) -- loss.py:7-15 (trainer.py:127-130): isin(data.C, ground_truth.C)

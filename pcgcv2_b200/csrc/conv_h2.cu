@@ -110,13 +110,14 @@ static int launch_octet_h2(const uint32_t *in, int in_ld, const int32_t *pnbr, i
     }
 }
 
-template <int COUT>
+template <int COUT, bool K1TAIL = false>
 static int launch_octet_h2c4(const uint32_t *in, int in_ld, const int32_t *pnbr, int64_t n_par, const uint32_t *packed, float inv_scale,
                              const float *bias, const float *res, int res_ld, float *out, int out_ld, uint32_t *out_h2,
-                             int out_h2_ld, int flags, int *overflow, cudaStream_t s) {
+                             int out_h2_ld, int flags, int *overflow, cudaStream_t s, const float *tail_w = nullptr,
+                             const float *tail_b = nullptr) {
     constexpr int RG = 2, WARPS = 8, MINB = 2;
     using C = OctetH2C4Cfg<COUT, RG, WARPS>;
-    auto kern = conv_k3_octet_h2c4_kernel<COUT, RG, WARPS, MINB>;
+    auto kern = conv_k3_octet_h2c4_kernel<COUT, RG, WARPS, MINB, K1TAIL>;
     static int ctas = 0;
     if (ctas == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
@@ -127,7 +128,7 @@ static int launch_octet_h2c4(const uint32_t *in, int in_ld, const int32_t *pnbr,
     }
     kern<<<grid_for(n_par, C::OCTETS_PER_CTA, ctas), C::THREADS, C::smem_bytes(), s>>>(in, in_ld, pnbr, n_par, packed, inv_scale, bias,
                                                                                      res, res_ld, out, out_ld, out_h2, out_h2_ld,
-                                                                                     flags | octet_tile_flag(), overflow);
+                                                                                     flags | octet_tile_flag(), overflow, tail_w, tail_b);
     return check_launch("conv_k3_octet_h2c4");
 }
 
@@ -336,6 +337,26 @@ int pcgc_convT_k2s2_h2_fwd(const uint32_t *in_h2, int32_t in_ld, int64_t n_in, c
 }
 
 int pcgc_conv_k3_octet_h2_supported(int32_t cin, int32_t cout) { return octet_h2_shape(cin, cout) ? 1 : 0; }
+
+int pcgc_conv_k3_octet_h2_k1_supported(int32_t cin, int32_t cmid, int32_t cout) { return cin == 4 && cmid == 4 && cout == 8 ? 1 : 0; }
+
+int pcgc_conv_k3_octet_h2_k1_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *parent_nbr, int64_t n_parents,
+                                 const uint32_t *packed, float inv_scale, const float *bias, int32_t cin, int32_t cmid,
+                                 const float *tail_weight, const float *tail_bias, int32_t cout, const float *residual, int32_t res_ld,
+                                 float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t *overflow, void *stream) {
+    PCGC_REQUIRE(n_parents >= 0 && 8 * n_parents < 0x7FFFFFFF && in_ld >= cin, "pcgc_conv_k3_octet_h2_k1_fwd: bad shape");
+    PCGC_REQUIRE(pcgc_conv_k3_octet_h2_k1_supported(cin, cmid, cout), "pcgc_conv_k3_octet_h2_k1_fwd: no kernel for %d -> %d -> %d", cin, cmid, cout);
+    if (n_parents == 0) return PCGC_OK;
+    PCGC_REQUIRE(in_h2 && parent_nbr && packed && tail_weight && (out || out_h2), "pcgc_conv_k3_octet_h2_k1_fwd: null pointer");
+    PCGC_REQUIRE((in_ld % 4 == 0) && (((uintptr_t)in_h2 & 15) == 0) && (((uintptr_t)packed & 15) == 0),
+                 "pcgc_conv_k3_octet_h2_k1_fwd: input rows must be 16-byte aligned (ld %% 4 == 0)");
+    PCGC_REQUIRE(!out || (out_ld >= cout && out_ld % 2 == 0 && ((uintptr_t)out & 7) == 0), "pcgc_conv_k3_octet_h2_k1_fwd: out must be 8-byte aligned");
+    PCGC_REQUIRE(!residual || (res_ld % 2 == 0 && ((uintptr_t)residual & 7) == 0), "pcgc_conv_k3_octet_h2_k1_fwd: residual must be 8-byte aligned");
+    PCGC_REQUIRE(!out_h2 || (out_h2_ld >= cout && out_h2_ld % 4 == 0 && ((uintptr_t)out_h2 & 15) == 0),
+                 "pcgc_conv_k3_octet_h2_k1_fwd: h2 output needs 16-byte aligned rows");
+    return launch_octet_h2c4<4, true>(in_h2, in_ld, parent_nbr, n_parents, packed, inv_scale, bias, residual, res_ld, out, out_ld, out_h2,
+                                      out_h2_ld, 0, overflow, (cudaStream_t)stream, tail_weight, tail_bias);
+}
 
 int pcgc_conv_k3_octet_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *parent_nbr, int64_t n_parents,
                               const uint32_t *packed, float inv_scale, const float *bias, int32_t cin, int32_t cout,

@@ -279,12 +279,18 @@ static __global__ void pack_weights_h2c4_kernel(const float *__restrict__ w, int
     }
 }
 
-template <int COUT, int RG, int WARPS, int MINB>
+// K1TAIL (COUT = 4 only): the k=1 convolution that follows the layer in the InceptionResNet block (conv1_2 after conv1_1,
+// autoencoder.py:55) runs in the epilogue: y = relu(conv_k3(x)) is never written; out = y W1 + b1 + residual with W1
+// [4][8] fp32 (`tail_w`), b1 [8] (`tail_b`).  A row's four values sit in lanes t = 0, 1 of its quad: four shuffles hand them
+// to all four lanes, lane t finishes output channels 2t, 2t+1 (8 FFMA) and stores the fp32 and the h2 pair.
+template <int COUT, int RG, int WARPS, int MINB, bool K1TAIL = false>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 conv_k3_octet_h2c4_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__restrict__ pnbr, int64_t n_par,
                           const uint32_t *__restrict__ packed, float inv_scale, const float *__restrict__ bias,
                           const float *__restrict__ residual, int res_ld, float *__restrict__ out, int out_ld,
-                          uint32_t *__restrict__ out_h2, int out_h2_ld, int flags, int *__restrict__ overflow) {
+                          uint32_t *__restrict__ out_h2, int out_h2_ld, int flags, int *__restrict__ overflow,
+                          const float *__restrict__ tail_w = nullptr, const float *__restrict__ tail_b = nullptr) {
+    static_assert(!K1TAIL || COUT == 4, "k=1 tail: 4 -> 8 only");
     using C = OctetH2C4Cfg<COUT, RG, WARPS>;
     constexpr int CT = C::CT, OW = C::OW, SY = C::SY, SZ = C::SZ, HB = C::HB, W_OFF = C::W_OFF;
     extern __shared__ __align__(128) unsigned char smem_oh2[];
@@ -303,7 +309,13 @@ conv_k3_octet_h2c4_kernel(const uint32_t *__restrict__ in, int in_ld, const int3
     const int64_t n_tiles = (n_par + C::OCTETS_PER_CTA - 1) / C::OCTETS_PER_CTA;
     const char *in_bytes = reinterpret_cast<const char *>(in);
     const uint32_t ldb = (uint32_t)in_ld * 4u;
-    H2Epilogue epi{bias, residual, out, out_h2, res_ld, out_ld, out_h2_ld, flags, inv_scale};
+    H2Epilogue epi{K1TAIL ? tail_b : bias, residual, out, out_h2, res_ld, out_ld, out_h2_ld, K1TAIL ? 0 : flags, K1TAIL ? 1.f : inv_scale};
+    float tw[4][2], b0 = 0.f, b1 = 0.f;                             // K1TAIL: W1[i][2t], W1[i][2t+1]; first-stage bias of this lane's pair
+    if constexpr (K1TAIL) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { tw[i][0] = __ldg(tail_w + i * 8 + 2 * t); tw[i][1] = __ldg(tail_w + i * 8 + 2 * t + 1); }
+        if (t < 2 && bias) { b0 = __ldg(bias + 2 * t); b1 = __ldg(bias + 2 * t + 1); }
+    }
     int32_t prow[OW];
     const bool chunked = flags & PCGC_TILES_CHUNKED;                // see conv_k3_octet_h2_kernel
     const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
@@ -358,18 +370,38 @@ conv_k3_octet_h2c4_kernel(const uint32_t *__restrict__ in, int in_ld, const int3
         }
 
         const int64_t n = n_par * 8, row0 = oct0 * 8;
-#pragma unroll
-        for (int c = 0; c < CT; ++c) {
-            const int co = 8 * c + 2 * t;
-            if (co >= COUT) continue;
+        if constexpr (K1TAIL) {
 #pragma unroll
             for (int r = 0; r < RG; ++r)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    // first stage on the lanes that own channels (t = 0: 0, 1; t = 1: 2, 3): scale, bias, ReLU
+                    const float v0 = fmaxf(acc[0][r][2 * h] * inv_scale + b0, 0.f), v1 = fmaxf(acc[0][r][2 * h + 1] * inv_scale + b1, 0.f);
+                    const int q0 = lane & ~3;
+                    const float c0 = __shfl_sync(0xffffffffu, v0, q0), c1 = __shfl_sync(0xffffffffu, v1, q0);
+                    const float c2 = __shfl_sync(0xffffffffu, v0, q0 + 1), c3 = __shfl_sync(0xffffffffu, v1, q0 + 1);
                     const int64_t row = row0 + 16 * r + 8 * h + g;
                     if (row >= n) continue;
-                    epi.store_pair(row, co, acc[c][r][2 * h], acc[c][r][2 * h + 1]);
+                    float y0 = c0 * tw[0][0], y1 = c0 * tw[0][1];
+                    y0 = fmaf(c1, tw[1][0], y0); y1 = fmaf(c1, tw[1][1], y1);
+                    y0 = fmaf(c2, tw[2][0], y0); y1 = fmaf(c2, tw[2][1], y1);
+                    y0 = fmaf(c3, tw[3][0], y0); y1 = fmaf(c3, tw[3][1], y1);
+                    epi.store_pair(row, 2 * t, y0, y1);               // + b1 + residual, fp32 and h2 stores
                 }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const int co = 8 * c + 2 * t;
+                if (co >= COUT) continue;
+#pragma unroll
+                for (int r = 0; r < RG; ++r)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int64_t row = row0 + 16 * r + 8 * h + g;
+                        if (row >= n) continue;
+                        epi.store_pair(row, co, acc[c][r][2 * h], acc[c][r][2 * h + 1]);
+                    }
+            }
         }
     }
     if (epi.over && overflow) *overflow = 1;

@@ -139,9 +139,20 @@ int pcgc_irn_fwd(const pcgc_irn_args *a, void *stream) {
             if (rc) return rc;
         }
     }
+    bool second_half_h2 = false;
+    if (a->reserved & PCGC_IRN_FUSED_TAIL) {                      // conv1_1 + ReLU + conv1_2 + residual in one kernel: cc is never written
+        if (a->route[2] != PCGC_ROUTE_H2_OCTET || !pcgc_conv_k3_octet_h2_k1_supported(q, q, h)) {
+            pcgc::set_error("pcgc_irn_fwd: fused tail needs the full-octet h2 route and a supported shape (%d -> %d -> %d)", q, q, h);
+            return PCGC_ERR_INVALID;
+        }
+        rc = pcgc_conv_k3_octet_h2_k1_fwd(b_h, ab_ld, a->parent_nbr, a->n / 8, (const uint32_t *)a->w3[2], a->inv_scale[2], a->b3[2], q, q,
+                                          a->w1[1], a->b1[1], h, a->x + h, a->x_ld, a->out + h, a->out_ld, want_h2 ? a->out_h2 + h : nullptr,
+                                          a->out_h2_ld, a->overflow, stream);
+        if (rc) return rc;
+        second_half_h2 = want_h2;
+    } else {
     rc = run_k3(a, 2, b_f, b_h, ab_ld, q, q, nullptr, 0, cc_f, q, nullptr, 0, PCGC_EPI_RELU, stream);
     if (rc) return rc;
-    bool second_half_h2 = false;
     if (want_h2 && pcgc_conv_h2out_supported(1, q, h)) {
         rc = pcgc_conv_k1_fwd_h2out(cc_f, q, a->n, a->w1[1], a->b1[1], q, h, a->x + h, a->x_ld, a->out + h, a->out_ld, a->out_h2 + h,
                                     a->out_h2_ld, 0, a->overflow, stream);
@@ -150,6 +161,7 @@ int pcgc_irn_fwd(const pcgc_irn_args *a, void *stream) {
         rc = pcgc_conv_k1_fwd(cc_f, q, a->n, a->w1[1], a->b1[1], q, h, a->x + h, a->x_ld, a->out + h, a->out_ld, 0, stream);
     }
     if (rc) return rc;
+    }
 
     // ---- the halves of the h2 copy that no producer wrote
     if (want_h2) {

@@ -224,7 +224,7 @@ def test_irn_block_per_c_call_is_the_same_computation(r3, use_h2):
     bit-identical bitstream, bottleneck and decoded set; with and without the h2 kernels; also without octet kernels."""
     pts = synth.ellipsoid_vox8()
     for octet in (True, False):
-        fused = Codec(r3, use_h2=use_h2, use_octet_kernels=octet, fuse_irn=True, merge_first=False)
+        fused = Codec(r3, use_h2=use_h2, use_octet_kernels=octet, fuse_irn=True, merge_first=False, fuse_tail=False)
         plain = Codec(r3, use_h2=use_h2, use_octet_kernels=octet, fuse_irn=False)
         a, b = fused.encode(pts), plain.encode(pts)
         assert a.F == b.F and a.H == b.H and (a.coords == b.coords).all() and fused._irn_plans and not plain._irn_plans
@@ -247,16 +247,18 @@ def test_tcgen05_routes_give_the_same_stream_and_occupancy(r3):
     assert plain.encode(pts).F == a.F and (canon(plain.decode(a)) == canon(da)).all()
 
 
-def test_merged_first_layers_of_the_16_channel_blocks(r3):
+@pytest.mark.parametrize("merge_first,fuse_tail", [(True, False), (False, True), (True, True)])
+def test_merged_first_layers_of_the_16_channel_blocks(r3, merge_first, fuse_tail):
     """conv0_0 (k=3) + conv1_0 (k=1) of the finest decoder blocks as ONE k=3 convolution 16 -> 8 (conv1_0's weights at the
-    centre offset, PCGC_IRN_MERGED_FIRST): the block output stays within the h2 tolerance of the layer-by-layer block, the
-    stream is untouched (the analysis network has no 16-channel block) and the decoded set is the same on the KAT cloud."""
+    centre offset, PCGC_IRN_MERGED_FIRST) and conv1_1 (k=3) + ReLU + conv1_2 (k=1) as one kernel (PCGC_IRN_FUSED_TAIL): the
+    block output stays within the h2 tolerance of the layer-by-layer block, the stream is untouched (the analysis network has
+    no 16-channel block) and the decoded set is the same on the KAT cloud."""
     pts = synth.ellipsoid_vox8()
-    merged, plain = Codec(r3, merge_first=True), Codec(r3, merge_first=False)
+    merged, plain = Codec(r3, merge_first=merge_first, fuse_tail=fuse_tail), Codec(r3, merge_first=False, fuse_tail=False)
     a, b = merged.encode(pts), plain.encode(pts)
     assert a.F == b.F and a.H == b.H and (a.coords == b.coords).all()
     da, db = merged.decode(a), plain.decode(b)
-    assert any(p["args"].reserved == 1 for p in merged._irn_plans.values())
+    assert any(p["args"].reserved == (1 if merge_first else 0) + (2 if fuse_tail else 0) for p in merged._irn_plans.values())
     assert not any(p["args"].reserved for p in plain._irn_plans.values())
     assert (canon(da) == canon(db)).all()
     # one block in isolation on random features over the finest decoder set of the KAT cloud
