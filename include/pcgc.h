@@ -161,16 +161,6 @@ int pcgc_conv_k3_pack_weights(const float *weight, int32_t cin, int32_t cout, fl
 int pcgc_conv_k3_fwd_packed(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, const float *packed,
                             const float *bias, int32_t cin, int32_t cout, const float *residual,
                             int32_t res_ld, float *out, int32_t out_ld, int32_t flags, void *stream);
-/* a3, EXPERIMENTAL tcgen05 variant (cin = 16, cout in {1,4,8,16}): warp-specialised persistent kernel,
- * gathered rows -> registers -> hi/lo split -> tcgen05.st into TENSOR MEMORY (A operand), weights in
- * shared memory (UMMA K-major descriptors), tcgen05.mma.kind::tf32 with TMEM accumulators (3xTF32, several
- * short accumulation chains joined by FADD in the epilogue).  Same results as pcgc_conv_k3_fwd_packed; at
- * round 1 it is slower (see profiles/r01_tcgen05_experiments.md), so nothing selects it by default. */
-size_t pcgc_conv_k3_tcgen05_packed_floats(int32_t cin, int32_t cout);
-int pcgc_conv_k3_tcgen05_pack_weights(const float *weight, int32_t cin, int32_t cout, float *packed, void *stream);
-int pcgc_conv_k3_fwd_tcgen05(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, const float *packed,
-                             const float *bias, int32_t cin, int32_t cout, const float *residual,
-                             int32_t res_ld, float *out, int32_t out_ld, int32_t flags, void *stream);
 /* a3 on FULL-OCTET sets (every set the synthesis network convolves on is the 8-child expansion of a parent
  * set, ME.MinkowskiGenerativeConvolutionTranspose autoencoder.py:155,182,209: n = 8 * n_parents rows, row
  * 8*i + c = child c = cx + 2cy + 4cz of parent row i).  The 4x4x4 voxel halo of each octet is staged in shared

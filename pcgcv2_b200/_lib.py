@@ -54,9 +54,6 @@ SIGNATURES = {
     "pcgc_conv_k3_packed_floats": (c_sz, [c_i32, c_i32]),
     "pcgc_conv_k3_pack_weights": (ctypes.c_int, [c_p, c_i32, c_i32, c_p, c_p]),
     "pcgc_conv_k3_fwd_packed": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),
-    "pcgc_conv_k3_tcgen05_packed_floats": (c_sz, [c_i32, c_i32]),
-    "pcgc_conv_k3_tcgen05_pack_weights": (ctypes.c_int, [c_p, c_i32, c_i32, c_p, c_p]),
-    "pcgc_conv_k3_fwd_tcgen05": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),
     "pcgc_conv_k3_octet_packed_floats": (c_sz, [c_i32, c_i32]),
     "pcgc_conv_k3_octet_pack_weights": (ctypes.c_int, [c_p, c_i32, c_i32, c_p, c_p]),
     "pcgc_conv_k3_octet_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p, c_i32, c_i32, c_p]),

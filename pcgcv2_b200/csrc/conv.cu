@@ -4,7 +4,6 @@
 #include "conv_dispatch.h"
 #include "conv_mma.cuh"
 #include "conv_pipe.cuh"
-#include "conv_tc05.cuh"
 
 namespace pcgc {
 
@@ -87,19 +86,6 @@ static int check_conv_args(const char *who, const void *in, const void *w, const
     return PCGC_OK;
 }
 
-template <int COUT>
-static int launch_tc05t(const float *in, int in_ld, const int32_t *nbr, int64_t n, const float *packed, const float *bias,
-                        const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s) {
-    using C = tc05::CfgT<16>;
-    auto kern = tc05::conv_k3_tc05t_kernel<16, COUT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) { set_error("tcgen05 conv: %s", cudaGetErrorString(e)); return PCGC_ERR_CUDA; }
-    const int64_t tiles = (n + C::TM - 1) / C::TM;
-    kern<<<(int)(tiles < kNumSMs ? tiles : kNumSMs), C::THREADS, C::SMEM, s>>>(in, in_ld, nbr, n, packed, bias, res, res_ld, out,
-                                                                              out_ld, flags);
-    return check_launch("conv_k3_tc05t");
-}
-
 extern "C" {
 
 int pcgc_conv_k3_fwd(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, const float *weight,
@@ -156,39 +142,6 @@ int pcgc_conv_k3_fwd_packed(const float *in, int32_t in_ld, const int32_t *nbr, 
 #undef CASE
     PCGC_REQUIRE(rc != kNotHandled, "pcgc_conv_k3_fwd_packed: unsupported shape %dx%d", cin, cout);
     return rc;
-}
-
-// ---- experimental: the same convolution on tcgen05 (UMMA, accumulators and the gathered operand in tensor memory)
-size_t pcgc_conv_k3_tcgen05_packed_floats(int32_t cin, int32_t cout) {
-    return (cin == 16 && cout >= 1 && cout <= 16) ? (size_t)27 * 2 * 16 * 16 : 0;
-}
-
-int pcgc_conv_k3_tcgen05_pack_weights(const float *weight, int32_t cin, int32_t cout, float *packed, void *stream) {
-    PCGC_REQUIRE(pcgc_conv_k3_tcgen05_packed_floats(cin, cout) > 0 && weight && packed,
-                 "pcgc_conv_k3_tcgen05_pack_weights: only cin = 16, cout <= 16 (got %dx%d)", cin, cout);
-    tc05::pack_weights_tc05t_kernel<16><<<32, 256, 0, (cudaStream_t)stream>>>(weight, cout, packed);
-    return check_launch("pack_weights_tc05t");
-}
-
-int pcgc_conv_k3_fwd_tcgen05(const float *in, int32_t in_ld, const int32_t *nbr, int64_t n, const float *packed,
-                             const float *bias, int32_t cin, int32_t cout, const float *residual, int32_t res_ld,
-                             float *out, int32_t out_ld, int32_t flags, void *stream) {
-    int rc = check_conv_args("pcgc_conv_k3_fwd_tcgen05", in, packed, out, n, cin, cout, in_ld, out_ld);
-    if (rc || n == 0) return rc;
-    PCGC_REQUIRE(nbr != nullptr && pcgc_conv_k3_tcgen05_packed_floats(cin, cout) > 0,
-                 "pcgc_conv_k3_fwd_tcgen05: only cin = 16, cout in {1, 4, 8, 16} (got %dx%d)", cin, cout);
-    PCGC_REQUIRE((in_ld % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)packed & 15) == 0),
-                 "pcgc_conv_k3_fwd_tcgen05: input rows must be 16-byte aligned");
-    cudaStream_t s = (cudaStream_t)stream;
-    switch (cout) {
-        case 16: return launch_tc05t<16>(in, in_ld, nbr, n, packed, bias, residual, res_ld, out, out_ld, flags, s);
-        case 8: return launch_tc05t<8>(in, in_ld, nbr, n, packed, bias, residual, res_ld, out, out_ld, flags, s);
-        case 4: return launch_tc05t<4>(in, in_ld, nbr, n, packed, bias, residual, res_ld, out, out_ld, flags, s);
-        case 1: return launch_tc05t<1>(in, in_ld, nbr, n, packed, bias, residual, res_ld, out, out_ld, flags, s);
-        default: break;
-    }
-    set_error("pcgc_conv_k3_fwd_tcgen05: cout %d has no instantiation", cout);
-    return PCGC_ERR_INVALID;
 }
 
 static int conv_k1_impl(const char *who, const float *in, int32_t in_ld, int64_t n, const float *weight, const float *bias,

@@ -263,31 +263,6 @@ def conv_k3_packed(feats, nbr, pw: PackedK3, bias=None, residual=None, relu=Fals
     return out
 
 
-class PackedK3Tcgen05:
-    """weights packed for the experimental tcgen05 kernel (cin = 16, cout <= 16)."""
-
-    def __init__(self, weight: torch.Tensor):
-        self.cin, self.cout = int(weight.shape[1]), int(weight.shape[2])
-        n = int(_lib.lib().pcgc_conv_k3_tcgen05_packed_floats(self.cin, self.cout))
-        self.packed = None
-        if n:
-            self.packed = torch.empty(n, dtype=torch.float32, device=weight.device)
-            check(_lib.lib().pcgc_conv_k3_tcgen05_pack_weights(_p(weight.contiguous()), self.cin, self.cout, _p(self.packed),
-                                                               _stream()), "pcgc_conv_k3_tcgen05_pack_weights")
-
-
-def conv_k3_tcgen05(feats, nbr, pw: PackedK3Tcgen05, bias=None, residual=None, relu=False, out=None):
-    feats = _feat(feats)
-    n, cin = feats.shape
-    assert cin == pw.cin and pw.packed is not None
-    out = _out_slice(out, n, pw.cout, feats.device)
-    residual = None if residual is None else _feat(residual)
-    check(_lib.lib().pcgc_conv_k3_fwd_tcgen05(_p(feats), feats.stride(0), _p(nbr), n, _p(pw.packed), _p(bias), cin, pw.cout,
-                                              _p(residual), 0 if residual is None else residual.stride(0), _p(out),
-                                              out.stride(0), EPI_RELU if relu else 0, _stream()), "pcgc_conv_k3_fwd_tcgen05")
-    return out
-
-
 class PackedK3Octet:
     """k=3 weights packed for the full-octet kernels (None if the shape has no such kernel)."""
 

@@ -231,27 +231,6 @@ def test_conv_k3_tensor_core_vs_oracle(cin, cout):
         assert _rel_err(got, S.conv_k3(f[:n], c[:n], 1, w, b)) < CONV_TOL
 
 
-@pytest.mark.parametrize("cout", [16, 4, 1])
-def test_conv_k3_tcgen05_vs_oracle(cout):
-    """experimental tcgen05 kernel (A operand and accumulators in tensor memory): same parity bar."""
-    c = _surface()[:30011]
-    keys = _keys(c)
-    nbr = ops.kernel_map_k3(keys, ops.HashTable(keys))
-    g = torch.Generator().manual_seed(cout)
-    f = torch.randn(len(c), 16, generator=g)
-    w = torch.randn(27, 16, cout, generator=g) / np.sqrt(27 * 16)
-    b = torch.randn(1, cout, generator=g)
-    ref = S.conv_k3(f, c, 1, w, b)
-    pw = ops.PackedK3Tcgen05(w.to(DEV))
-    got = ops.conv_k3_tcgen05(f.to(DEV), nbr, pw, b.to(DEV))
-    assert _rel_err(got, ref) < CONV_TOL
-    for n in (1, 127, 129, 4097):                                 # tile tails, fewer tiles than SMs
-        kk = _keys(c[:n])
-        nb = ops.kernel_map_k3(kk, ops.HashTable(kk))
-        got = ops.conv_k3_tcgen05(f[:n].to(DEV), nb, pw, b.to(DEV), relu=True)
-        assert _rel_err(got, torch.relu(S.conv_k3(f[:n], c[:n], 1, w, b))) < CONV_TOL
-
-
 OCTET_SHAPES = [(16, 16), (16, 8), (16, 4), (16, 1), (8, 16), (8, 8), (8, 4), (8, 1), (4, 8), (4, 4)]
 
 
