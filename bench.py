@@ -182,8 +182,12 @@ def run_ours(args, rank, world, local_rank):
     torch.set_num_threads(1)                                  # the frame threads are the parallelism; no intra-op pools per rank
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    stdout_fd = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line only:
+        sys.stdout.flush()                                          # NCCL prints its version banner to fd 1 whatever the debug
+        stdout_fd = os.dup(1)                                       # file says, so fd 1 points at stderr until the line is printed
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     peaks = {}
     try:
@@ -192,23 +196,32 @@ def run_ours(args, rank, world, local_rank):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
-    # config 3: every rank codes its own jittered cloud; --same-frames gives every rank rank 0's cloud (separates frame-size
-    # variance from host contention in the scaling numbers)
-    seed = 0 if args.same_frames else rank
-    pts = synth.synthetic_vox10(seed=seed, jitter=0.1 if (world > 1 and not args.same_frames) else 0.0)   # N=1: 795 124 voxels
-    n0 = len(pts)
+    # N = 1: BASELINE config 2's stand-in, synthetic_vox10(0), 795 124 voxels, in every slot.  N > 1: config 3's four jittered
+    # clouds (seeds 0-3, radii +-10 %: 690-840 k voxels); the `depth` frames a rank keeps in flight are clouds (rank + j) mod 4,
+    # so with the default depth of 4 every rank codes all four clouds each step (rotated) and the ranks carry equal work --
+    # round 1 gave rank r cloud r only, and the max-over-ranks time then measured the largest cloud, not the scaling.
+    # --same-frames gives every slot of every rank seed 0's unjittered cloud.
     depth = max(1, args.depth)
+    if world > 1 and not args.same_frames:
+        clouds = [synth.synthetic_vox10(seed=s, jitter=0.1) for s in range(4)]
+        frames_np = [clouds[(rank + j) % 4] for j in range(depth)]
+    else:
+        frames_np = [synth.synthetic_vox10(seed=0)] * depth
+    pts = frames_np[0]
+    n0 = len(pts)
+    step_points = sum(len(f) for f in frames_np)
     sd = load_weights("r3")
     pipe = FramePipeline(sd, device=dev, depth=depth, coord_bits=10)   # `depth` frames in flight on this GPU; vox10: --res 1024
     codec = pipe.codecs[0]
-    host_coords = torch.from_numpy(pts).pin_memory()
-    dev_coords = host_coords.to(dev)
+    host_frames = [torch.from_numpy(f).pin_memory() for f in frames_np]
+    dev_frames = [h.to(dev) for h in host_frames]
+    host_coords, dev_coords = host_frames[0], dev_frames[0]
 
     def step_device():                                       # inputs resident in HBM, result left on the device
-        return pipe.roundtrip([dev_coords] * depth, to_host=False)[-1]
+        return pipe.roundtrip(dev_frames, to_host=False)[0]
 
     def step_e2e():                                          # public API with HOST buffers: H2D and D2H inside
-        return pipe.roundtrip([host_coords] * depth, to_host=True, copy=False)[-1]
+        return pipe.roundtrip(host_frames, to_host=True, copy=False)[0]
 
     def step_serial():                                       # one frame at a time on one stream (latency view)
         st = codec.encode(dev_coords)
@@ -267,8 +280,10 @@ def run_ours(args, rank, world, local_rank):
     pipe.close()
 
     # the path's only collective: per-rank counters
-    mine = [n0 * depth, st.bits() * depth, out.shape[0], 8 * len(st.F) * depth, 8 * len(st.C or b"") * depth,
-            int(round(1e3 * ms_own / args.steps)), int(round(1e3 * ms_e2e_own / args.steps)), n0]
+    # (bits are those of slot 0's cloud, scaled to the step's points: the other slots' streams are not kept)
+    scale_bits = step_points / n0
+    mine = [step_points, int(st.bits() * scale_bits), out.shape[0], int(8 * len(st.F) * scale_bits), int(8 * len(st.C or b"") * scale_bits),
+            int(round(1e3 * ms_own / args.steps)), int(round(1e3 * ms_e2e_own / args.steps)), step_points]
     counters = pdist.gather_counters(torch.tensor(mine, dtype=torch.int64, device=dev))
     total_pts, total_bits = int(counters[:, 0].sum()), int(counters[:, 1].sum())
     if rank != 0:
@@ -301,9 +316,12 @@ def run_ours(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (emulated on the tensor cores: operands f16 hi + f16 lo = 22 significand bits, f32 accumulation)",
         "data": "synthetic",
-        "config": {"workload": "synthetic_vox10(seed=rank) full 3-scale encode+decode, r3 weights, rho=1 "
-                               "(stand-in for longdress_vox10_1300.ply)" + (" [--same-frames: every rank codes seed 0]" if args.same_frames else ""),
-                   "points_per_frame": n0, "frames_per_step": world * depth,
+        "config": {"workload": ("synthetic_vox10(seed=0) full 3-scale encode+decode, r3 weights, rho=1 (stand-in for longdress_vox10_1300.ply)"
+                                if (world == 1 or args.same_frames) else
+                                "config 3: the four jittered synthetic_vox10 clouds (seeds 0-3), full 3-scale encode+decode, r3 weights, rho=1; "
+                                "rank r keeps clouds (r + j) mod 4, j < depth, in flight, i.e. every rank codes all four each step"),
+                   "points_per_frame": n0 if (world == 1 or args.same_frames) else [len(c) for c in clouds],
+                   "frames_per_step": world * depth,
                    "parallelism": f"frames sharded over {world} GPU(s), {depth} frame(s) in flight per GPU (one host thread + "
                                   "CUDA stream each: the host range coder of one frame overlaps the kernels of the other)",
                    "serial_ms_per_frame": round(ms_serial / args.steps, 3), "host_cpus": len(os.sched_getaffinity(0)),
@@ -320,13 +338,13 @@ def run_ours(args, rank, world, local_rank):
                    "cdf_table": "built on the host once per symbol range and cached: after warm-up no table work is left in the timed region",
                    "per_rank": {"ms_per_step": [round(v / 1e3, 3) for v in counters[:, 5].tolist()],
                                 "e2e_ms_per_step": [round(v / 1e3, 3) for v in counters[:, 6].tolist()],
-                                "points_per_frame": counters[:, 7].tolist()},
+                                "points_per_step": counters[:, 7].tolist()},
                    "l2": "per-step traffic (~8.6 GB algorithmic, >1 GB live) exceeds the 126 MB L2; no flush needed"},
         # H2D: input voxels + (decode side) bottleneck coordinates and int16 symbols;
         # D2H: decoded voxels + (encode side) bottleneck coordinates and int16 symbols
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT,
-                "h2d_bytes_per_step": depth * int(host_coords.numel() * 4 + st.coords.size * 4 + st.coords.shape[0] * 8 * 2),
-                "d2h_bytes_per_step": depth * int(out.shape[0] * 3 * 4 + st.coords.size * 4 + st.coords.shape[0] * 8 * 2)},
+                "h2d_bytes_per_step": int(step_points * 12 + depth * (st.coords.size * 4 + st.coords.shape[0] * 8 * 2)),
+                "d2h_bytes_per_step": int(step_points * 12 + depth * (st.coords.size * 4 + st.coords.shape[0] * 8 * 2))},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", **dom, "peak": hbm_peak, "peak_source": peak_src,
@@ -346,6 +364,9 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:                                 # the reference install is optional on the box
             line["config"]["reference_equivalent_wall_ms"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         line["cpu_baseline"] = cpu_baseline(1, full_size=True)
+    if stdout_fd is not None:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

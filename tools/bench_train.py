@@ -6,6 +6,7 @@ backward (deterministic weight gradients), bucketed gradient all-reduce over NCC
 optimizer step.  Weak scaling: every rank trains on its own batch.  Prints one JSON line (rank 0)."""
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -23,8 +24,12 @@ def run(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    stdout_fd = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)                                  # NCCL's version banner goes to fd 1: keep stdout for the JSON line
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)                                       # identical replicas
     model = PCCModel().to(dev).train()
@@ -74,6 +79,9 @@ def run(args, rank, world, local_rank):
                         "h2d_bytes_per_step": int(np.mean([c.numel() * 4 + f.numel() * 4 for c, f in host])), "d2h_bytes_per_step": 4,
                         "note": "the timed step is already end to end: pinned host batch in, loss scalar out"},
                 "gpu_launches": int(launches)}
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     bucket.close()
     if world > 1:
