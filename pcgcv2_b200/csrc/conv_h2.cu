@@ -12,10 +12,10 @@ namespace pcgc {
 template <int CIN, int COUT>
 struct H2Tune {
     static constexpr bool NT = COUT < 16;
-    static constexpr int RG = NT ? (CIN == 32 ? 2 : 1) : (CIN == 16 && COUT == 16 ? 4 : 2);
-    static constexpr int D = NT ? (CIN == 16 ? 3 : 2) : (CIN == 64 ? 1 : 2);
+    static constexpr int RG = NT ? (CIN == 32 ? 2 : 1) : ((CIN == 16 && COUT == 16) || CIN == 8 ? 4 : 2);
+    static constexpr int D = NT ? (CIN <= 16 ? 3 : 2) : (CIN == 64 ? 1 : 2);
     static constexpr int WARPS = (!NT && CIN * COUT >= 1024) ? 16 : 8;
-    static constexpr int MINB = NT ? (CIN == 16 ? 4 : 2) : (WARPS == 16 ? 1 : 2);
+    static constexpr int MINB = NT ? (CIN <= 16 ? 4 : 2) : (WARPS == 16 ? 1 : 2);
 };
 
 template <int CIN, int COUT>
@@ -54,7 +54,7 @@ struct OctetH2Tune {
     // extra weight reads cost more; kept selectable for the next round's CTA-shared halo work.
     static constexpr bool DB = V != 0;
     static constexpr int RG = DB ? (NT ? 1 : 2) : (NT ? 2 : (COUT == 16 ? 4 : 2));
-    static constexpr int WARPS = DB ? (V == 1 ? 10 : 8) : (NT ? 8 : (COUT == 16 ? 8 : 16));
+    static constexpr int WARPS = DB ? (V == 1 ? 10 : 8) : (NT ? (CIN == 8 ? 16 : 8) : (COUT == 16 ? (CIN == 8 ? 12 : 8) : 16));
 };
 
 // PCGC_OCTET_TILE_ORDER=0 keeps the strided tile order; default 1 = one contiguous run of tiles per CTA
@@ -134,7 +134,8 @@ static int launch_octet_h2c4(const uint32_t *in, int in_ld, const int32_t *pnbr,
 
 static bool octet_h2c4_shape(int cin, int cout) { return cin == 4 && (cout == 4 || cout == 8); }
 static bool octet_h2_shape(int cin, int cout) {
-    return (cin == 16 && (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32)) || octet_h2c4_shape(cin, cout);
+    return (cin == 16 && (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32)) || (cin == 8 && (cout == 8 || cout == 16)) ||
+           octet_h2c4_shape(cin, cout);
 }
 
 // k=2 stride-2 convolution = the gather kernel over the 8 child slots of every parent (KV = 8, T formulation)
@@ -185,6 +186,7 @@ static bool down_h2_shape(int cin, int cout) { return (cin == 16 && cout == 32) 
 static bool up_h2_shape(int cin, int cout) { return (cin == 16 || cin == 32 || cin == 64) && cout % 2 == 0 && 8 * cout <= 512 && (8 * cout) % 16 == 0; }
 
 static bool h2_shape(int cin, int cout) {
+    if (cin == 8) return cout == 8 || cout == 16;
     if (cin == 16) return cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32;
     if (cin == 32) return cout == 1 || cout == 4 || cout == 8 || cout == 32;
     if (cin == 64) return cout == 1 || cout == 8 || cout == 16;
@@ -220,7 +222,8 @@ int pcgc_join_h2(const uint32_t *in_h2, int32_t in_ld, int64_t n, int32_t c, flo
 size_t pcgc_conv_k3_h2_packed_words(int32_t cin, int32_t cout) {
     if (octet_h2c4_shape(cin, cout)) return (size_t)27 * ((cout + 7) / 8) * 64;      // full-octet kernel only
     if (!h2_shape(cin, cout)) return 0;
-    return cout < 16 ? (size_t)27 * (cin / 16) * ((cout + 7) / 8) * 128 : (size_t)27 * (cin / 16) * (cout / 16) * 256;
+    const int ks = cin == 8 ? 1 : cin / 16;                                          // cin 8: [hi | lo] fill one k-step
+    return cout < 16 ? (size_t)27 * ks * ((cout + 7) / 8) * 128 : (size_t)27 * ks * (cout / 16) * 256;
 }
 
 int pcgc_conv_k3_h2_pack_weights(const float *weight, int32_t cin, int32_t cout, float scale, uint32_t *packed, void *stream) {
@@ -230,6 +233,11 @@ int pcgc_conv_k3_h2_pack_weights(const float *weight, int32_t cin, int32_t cout,
     if (octet_h2c4_shape(cin, cout)) {
         pack_weights_h2c4_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(weight, cout, scale, packed);
         return check_launch("pack_weights_h2c4");
+    }
+    if (cin == 8) {
+        pack_weights_h2c8_kernel<<<grid_for((int64_t)total / 2, 256, 4), 256, 0, (cudaStream_t)stream>>>(weight, 27, cout, cout < 16 ? 1 : 0, scale,
+                                                                                                      packed);
+        return check_launch("pack_weights_h2c8");
     }
     pack_weights_h2_kernel<<<grid_for((int64_t)total / 2, 256, 4), 256, 0, (cudaStream_t)stream>>>(weight, 27, cin, cout, cout < 16 ? 1 : 0,
                                                                                                 scale, packed);
@@ -258,7 +266,7 @@ int pcgc_conv_k3_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_t *nbr
     cudaStream_t s = (cudaStream_t)stream;
 #define H2(CI, CO) \
     if (cin == CI && cout == CO) return launch_h2<CI, CO>(in_h2, in_ld, nbr, n, packed, inv_scale, bias, residual, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
-    H2(16, 1) H2(16, 4) H2(16, 8) H2(16, 16) H2(16, 32) H2(32, 1) H2(32, 4) H2(32, 8) H2(32, 32) H2(64, 1) H2(64, 8) H2(64, 16)
+    H2(8, 8) H2(8, 16) H2(16, 1) H2(16, 4) H2(16, 8) H2(16, 16) H2(16, 32) H2(32, 1) H2(32, 4) H2(32, 8) H2(32, 32) H2(64, 1) H2(64, 8) H2(64, 16)
 #undef H2
     set_error("pcgc_conv_k3_h2_fwd: shape %dx%d has no instantiation", cin, cout);
     return PCGC_ERR_INVALID;
@@ -380,7 +388,7 @@ int pcgc_conv_k3_octet_h2_fwd(const uint32_t *in_h2, int32_t in_ld, const int32_
     cudaStream_t s = (cudaStream_t)stream;
 #define OH2(CI, CO) \
     if (cin == CI && cout == CO) return launch_octet_h2<CI, CO>(in_h2, in_ld, parent_nbr, n_parents, packed, inv_scale, bias, residual, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
-    OH2(16, 1) OH2(16, 4) OH2(16, 8) OH2(16, 16) OH2(16, 32)
+    OH2(8, 8) OH2(8, 16) OH2(16, 1) OH2(16, 4) OH2(16, 8) OH2(16, 16) OH2(16, 32)
 #undef OH2
     if (cin == 4 && cout == 8) return launch_octet_h2c4<8>(in_h2, in_ld, parent_nbr, n_parents, packed, inv_scale, bias, residual, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);
     if (cin == 4 && cout == 4) return launch_octet_h2c4<4>(in_h2, in_ld, parent_nbr, n_parents, packed, inv_scale, bias, residual, res_ld, out, out_ld, out_h2, out_h2_ld, flags, overflow, s);

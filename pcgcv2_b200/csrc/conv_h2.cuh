@@ -91,10 +91,11 @@ static __global__ void join_h2_kernel(const uint32_t *__restrict__ in, int in_ld
 template <int CIN, int COUT, bool NT_, int RG_, int D_, int WARPS_, int KV_ = 27>
 struct H2Cfg {
     static constexpr int KV = KV_;                                    // kernel volume: 27 (k=3) or 8 (k=2 stride 2: child slots)
-    static_assert(CIN % 16 == 0, "h2 kernel: CIN must be a multiple of 16");
+    static_assert(CIN % 16 == 0 || CIN == 8, "h2 kernel: CIN must be 8 or a multiple of 16");
     static_assert(NT_ || COUT % 16 == 0, "h2 kernel, T formulation: COUT must be a multiple of 16");
     static constexpr bool NT = NT_;
-    static constexpr int KS = CIN / 16;                               // k-steps (16 channels) per offset
+    static constexpr bool C8 = CIN == 8;                              // 8 channels: [hi | lo] of a row fill ONE k-step (see below)
+    static constexpr int KS = C8 ? 1 : CIN / 16;                      // k-steps (16 contraction slots) per offset
     static constexpr int CT = NT ? (COUT + 7) / 8 : COUT / 16;        // output-channel tiles (N=8 / M=16)
     static constexpr int RG = RG_, D = D_, WARPS = WARPS_;
     static constexpr int GROUP_ROWS = NT ? 16 : 8;
@@ -137,6 +138,50 @@ static __global__ void pack_weights_h2_kernel(const float *__restrict__ w, int k
             dst[2 + e] = lo;
         } else {
             uint32_t *dst = packed + (((int64_t)k * KS + q) * CT + c) * 256 + lane * 4 + e;
+            dst[0] = hi;
+            dst[128] = lo;
+        }
+    }
+}
+
+// ---- CIN = 8 ------------------------------------------------------------------------------------------------------
+// An h2 row of eight channels is 32 bytes = the words {hi01 hi23 lo01 lo23 | hi45 hi67 lo45 lo67}.  Lane (g, t) loads the
+// 8 bytes at word 2t: t = 0: (hi01, hi23), t = 1: (lo01, lo23), t = 2: (hi45, hi67), t = 3: (lo45, lo67) -- its two
+// m16n8k16 fragment registers (contraction slots 2t, 2t+1 and 2t+8, 2t+9).  The sixteen slots of ONE k-step so carry the hi
+// AND the lo halves of all eight channels, and the split product needs two MMAs per offset instead of three:
+//     MMA A: weights W_hi against every slot          -> W_hi x_hi + W_hi x_lo
+//     MMA B: weights W_lo against the hi slots, 0 against the lo slots -> W_lo x_hi
+// both chained from zero per kernel offset and joined to the running sum by a round-to-nearest FADD.
+// slot pair (2t, 2t+1) holds channels P(t) = {0, 0, 4, 4}[t], pair (2t+8, 2t+9) channels Q(t) = {2, 2, 6, 6}[t]; odd t = lo halves.
+// T packing:  [kvol][CT][2 (A, B)][32 lanes] x uint4 {a0, a1, a2, a3}: a0 = (W[P], W[P+1])[16c+g], a1 = same, cout 16c+g+8,
+//             a2 / a3 = channels Q, Q+1
+// NT packing: [kvol][CT][32 lanes] x uint4 {b0 A, b1 A, b0 B, b1 B}: b0 = (W[P], W[P+1])[8c+g], b1 = (W[Q], W[Q+1])[8c+g]
+static __global__ void pack_weights_h2c8_kernel(const float *__restrict__ w, int kvol, int cout, int nt, float scale,
+                                                uint32_t *__restrict__ packed) {
+    const int CT = nt ? (cout + 7) / 8 : cout / 16;
+    const int per_lane = nt ? 2 : 4;
+    const int64_t total = (int64_t)kvol * CT * 32 * per_lane;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i % per_lane), lane = (int)((i / per_lane) & 31);
+        int64_t r = i / (per_lane * 32);
+        const int c = (int)(r % CT);
+        const int k = (int)(r / CT);
+        const int g = lane >> 2, t = lane & 3;
+        const int P = (t >> 1) * 4, Q = P + 2;
+        int ci, co;
+        if (nt) { ci = e ? Q : P; co = 8 * c + g; }
+        else { ci = (e >> 1) ? Q : P; co = 16 * c + g + 8 * (e & 1); }
+        const float x0 = co < cout ? w[((int64_t)k * 8 + ci) * cout + co] * scale : 0.f;
+        const float x1 = co < cout ? w[((int64_t)k * 8 + ci + 1) * cout + co] * scale : 0.f;
+        uint32_t hi, lo;
+        split_pair_h2(x0, x1, hi, lo);
+        if (t & 1) lo = 0u;                                           // MMA B: W_lo only against the hi slots
+        if (nt) {
+            uint32_t *dst = packed + (((int64_t)k * CT + c) * 32 + lane) * 4;
+            dst[e] = hi;
+            dst[2 + e] = lo;
+        } else {
+            uint32_t *dst = packed + ((int64_t)k * CT + c) * 256 + lane * 4 + e;
             dst[0] = hi;
             dst[128] = lo;
         }
@@ -197,6 +242,7 @@ conv_k3_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__r
                   uint32_t *__restrict__ out_h2, int out_h2_ld, int flags, int *__restrict__ overflow) {
     using C = H2Cfg<CIN, COUT, NT, RG, D, WARPS, KV>;
     constexpr int KS = C::KS, CT = C::CT, NR = C::NR, RPW = C::RPW, W_OFF = C::W_OFF;
+    constexpr bool C8 = C::C8;
     constexpr bool IDXV = NR == 2 || NR == 4;                         // lane's NR kernel-map entries adjacent in smem
     extern __shared__ __align__(16) uint32_t wsm_h2[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -208,7 +254,7 @@ conv_k3_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__r
     __syncthreads();
 
     // gathered-row addressing: kernel-map entries are staged as row offsets in 16-byte units (in_ld % 4 == 0)
-    const char *in_lane = reinterpret_cast<const char *>(in + 4 * t);
+    const char *in_lane = reinterpret_cast<const char *>(in + (C8 ? 2 : 4) * t);
     const int32_t ld16 = in_ld >> 2;
     const int64_t n_tiles = (n + C::ROWS_PER_CTA - 1) / C::ROWS_PER_CTA;
     H2Epilogue epi{bias, residual, out, out_h2, res_ld, out_ld, out_h2_ld, flags, inv_scale};
@@ -271,7 +317,12 @@ conv_k3_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__r
 #pragma unroll
                 for (int q = 0; q < KS; ++q) {
                     const char *src = in_lane + (uint64_t)(uint32_t)id[j] * 16u + 64 * q;
-                    x[st][j][q] = ok ? __ldg(reinterpret_cast<const uint4 *>(src)) : make_uint4(0u, 0u, 0u, 0u);
+                    if constexpr (C8) {                               // 8 bytes per lane: the row's two fragment registers
+                        const uint2 v = ok ? __ldg(reinterpret_cast<const uint2 *>(src)) : make_uint2(0u, 0u);
+                        x[st][j][q] = make_uint4(v.x, v.y, 0u, 0u);
+                    } else {
+                        x[st][j][q] = ok ? __ldg(reinterpret_cast<const uint4 *>(src)) : make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
             }
         };
@@ -280,7 +331,28 @@ conv_k3_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__r
             float part[CT][RG][4];
 #pragma unroll
             for (int q = 0; q < KS; ++q) {
-                if constexpr (NT) {
+                if constexpr (C8 && NT) {
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) {
+                        const uint4 w = *reinterpret_cast<const uint4 *>(wb + (c * 32 + lane) * 4);
+#pragma unroll
+                        for (int r = 0; r < RG; ++r)
+                            mma_f16_zero(part[c][r], x[st][2 * r][0].x, x[st][2 * r + 1][0].x, x[st][2 * r][0].y, x[st][2 * r + 1][0].y, w.x, w.y);
+#pragma unroll
+                        for (int r = 0; r < RG; ++r)
+                            mma_f16(part[c][r], x[st][2 * r][0].x, x[st][2 * r + 1][0].x, x[st][2 * r][0].y, x[st][2 * r + 1][0].y, w.z, w.w);
+                    }
+                } else if constexpr (C8) {
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) {
+                        const uint4 *wp = reinterpret_cast<const uint4 *>(wb + c * 256) + lane;
+                        const uint4 wa = wp[0], wl = wp[32];
+#pragma unroll
+                        for (int r = 0; r < RG; ++r) mma_f16_zero(part[c][r], wa.x, wa.y, wa.z, wa.w, x[st][r][0].x, x[st][r][0].y);
+#pragma unroll
+                        for (int r = 0; r < RG; ++r) mma_f16(part[c][r], wl.x, wl.y, wl.z, wl.w, x[st][r][0].x, x[st][r][0].y);
+                    }
+                } else if constexpr (NT) {
                     uint4 w[CT];
 #pragma unroll
                     for (int c = 0; c < CT; ++c) w[c] = *reinterpret_cast<const uint4 *>(wb + ((q * CT + c) * 32 + lane) * 4);

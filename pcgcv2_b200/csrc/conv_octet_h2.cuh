@@ -16,17 +16,18 @@ namespace pcgc {
 template <int CIN, int COUT, bool NT_, int RG_, int WARPS_, bool DB_ = false>
 struct OctetH2Cfg {
     static constexpr bool DB = DB_;                               // two halo buffers per warp: the next tile is staged during the MMAs
-    static_assert(CIN == 16 || CIN == 32, "octet h2 kernel: CIN in {16, 32}");
+    static_assert(CIN == 8 || CIN == 16 || CIN == 32, "octet h2 kernel: CIN in {8, 16, 32}");
     static_assert(NT_ || COUT % 16 == 0, "octet h2 kernel, T formulation: COUT must be a multiple of 16");
     static constexpr bool NT = NT_;
-    static constexpr int KS = CIN / 16;                           // k-steps = 64-byte chunks per row
+    static constexpr bool C8 = CIN == 8;                          // 32-byte rows: [hi | lo] of the 8 channels = one k-step (conv_h2.cuh)
+    static constexpr int KS = C8 ? 1 : CIN / 16;                  // k-steps = 64-byte chunks per row
     static constexpr int CT = NT ? (COUT + 7) / 8 : COUT / 16;
     static constexpr int RG = RG_, WARPS = WARPS_, THREADS = 32 * WARPS_;
     static constexpr int OW = NT ? 2 * RG : RG;                   // octets per warp iteration
     static constexpr int NR = OW;                                 // halo rows read per lane per offset
     static constexpr int ROWB = CIN * 4;
     static constexpr int PPR = CIN / 4;
-    static constexpr int SY = 4, SZ = 4 * SY;
+    static constexpr int SY = C8 ? 6 : 4, SZ = 4 * SY;            // CIN 8: y rows 16 banks apart (LDS.64 of rows {0,1,6,7} is conflict free)
     static constexpr int HROWS = 3 * SZ + 3 * SY + 4;
     static constexpr int HB = HROWS * ROWB;
     static constexpr int W_OFF = KS * CT * (NT ? 128 : 256);
@@ -56,6 +57,7 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
     using C = OctetH2Cfg<CIN, COUT, NT, RG, WARPS, DB>;
     constexpr int KS = C::KS, CT = C::CT, OW = C::OW, NR = C::NR, ROWB = C::ROWB, PPR = C::PPR;
     constexpr int SY = C::SY, SZ = C::SZ, HB = C::HB, W_OFF = C::W_OFF;
+    constexpr bool C8 = C::C8;
     extern __shared__ __align__(128) unsigned char smem_oh2[];
     uint32_t *wsm = reinterpret_cast<uint32_t *>(smem_oh2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -70,7 +72,7 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
     const int cx = g & 1, cy = (g >> 1) & 1, cz = g >> 2;
     int slot[KS];                                                   // byte offsets inside a halo buffer
 #pragma unroll
-    for (int s = 0; s < KS; ++s) slot[s] = (cx + SY * cy + SZ * cz) * ROWB + (KS >= 2 ? ((s ^ cx) * 64) : 0) + t * 16;
+    for (int s = 0; s < KS; ++s) slot[s] = (cx + SY * cy + SZ * cz) * ROWB + (KS >= 2 ? ((s ^ cx) * 64) : 0) + t * (C8 ? 8 : 16);
 
     const int64_t n_tiles = (n_par + C::OCTETS_PER_CTA - 1) / C::OCTETS_PER_CTA;
     const char *in_bytes = reinterpret_cast<const char *>(in);
@@ -130,8 +132,14 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
 #pragma unroll
             for (int j = 0; j < NR; ++j)
 #pragma unroll
-                for (int q = 0; q < KS; ++q)
-                    x[j][q] = *reinterpret_cast<const uint4 *>(halo + slot[KS >= 2 ? (q ^ (ix & 1)) : 0] + j * HB + doff);
+                for (int q = 0; q < KS; ++q) {
+                    if constexpr (C8) {
+                        const uint2 v = *reinterpret_cast<const uint2 *>(halo + slot[0] + j * HB + doff);
+                        x[j][q] = make_uint4(v.x, v.y, 0u, 0u);
+                    } else {
+                        x[j][q] = *reinterpret_cast<const uint4 *>(halo + slot[KS >= 2 ? (q ^ (ix & 1)) : 0] + j * HB + doff);
+                    }
+                }
         };
         load_frags(0, xb[0]);
 #pragma unroll
@@ -143,7 +151,28 @@ conv_k3_octet_h2_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_
             float part[CT][RG][4];
 #pragma unroll
             for (int q = 0; q < KS; ++q) {
-                if constexpr (NT) {
+                if constexpr (C8 && NT) {                                                              // two MMAs per offset (conv_h2.cuh)
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) {
+                        const uint4 w = *reinterpret_cast<const uint4 *>(wb + (c * 32 + lane) * 4);
+#pragma unroll
+                        for (int r = 0; r < RG; ++r)
+                            mma_f16_zero(part[c][r], x[2 * r][0].x, x[2 * r + 1][0].x, x[2 * r][0].y, x[2 * r + 1][0].y, w.x, w.y);
+#pragma unroll
+                        for (int r = 0; r < RG; ++r)
+                            mma_f16(part[c][r], x[2 * r][0].x, x[2 * r + 1][0].x, x[2 * r][0].y, x[2 * r + 1][0].y, w.z, w.w);
+                    }
+                } else if constexpr (C8) {
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) {
+                        const uint4 *wp = reinterpret_cast<const uint4 *>(wb + c * 256) + lane;
+                        const uint4 wa = wp[0], wl = wp[32];
+#pragma unroll
+                        for (int r = 0; r < RG; ++r) mma_f16_zero(part[c][r], wa.x, wa.y, wa.z, wa.w, x[r][0].x, x[r][0].y);
+#pragma unroll
+                        for (int r = 0; r < RG; ++r) mma_f16(part[c][r], wl.x, wl.y, wl.z, wl.w, x[r][0].x, x[r][0].y);
+                    }
+                } else if constexpr (NT) {
                     uint4 w[CT];
 #pragma unroll
                     for (int c = 0; c < CT; ++c) w[c] = *reinterpret_cast<const uint4 *>(wb + ((q * CT + c) * 32 + lane) * 4);

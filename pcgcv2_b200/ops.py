@@ -329,7 +329,7 @@ class PackedK3H2:
     @property
     def gather(self) -> bool:
         """a child-map (gather) kernel exists for the shape; cin = 4 has the full-octet kernel only."""
-        return self.cin % 16 == 0
+        return self.cin % 16 == 0 or self.cin == 8
 
     def __init__(self, weight: torch.Tensor):
         assert weight.dim() == 3 and weight.shape[0] == 27 and weight.is_contiguous()

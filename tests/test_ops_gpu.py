@@ -290,7 +290,7 @@ def test_conv_k3_octet_equals_child_map_kernels():
             assert float((got - want).abs().max() / want.abs().max()) < 2e-6
 
 
-H2_SHAPES = [(16, 1), (16, 4), (16, 8), (16, 16), (16, 32), (32, 1), (32, 4), (32, 8), (32, 32), (64, 1), (64, 8), (64, 16)]
+H2_SHAPES = [(8, 8), (8, 16), (16, 1), (16, 4), (16, 8), (16, 16), (16, 32), (32, 1), (32, 4), (32, 8), (32, 32), (64, 1), (64, 8), (64, 16)]
 H2_TOL = 3e-6                                                     # 22-bit operands: two orders below CONV_TOL
 
 
@@ -404,7 +404,7 @@ def test_conv_k3_wide_tcgen05_vs_oracle(cin, cout):
         assert _rel_err(got, torch.relu(S.conv_k3(f[:n], cc, 1, w, b))) < H2_TOL
 
 
-@pytest.mark.parametrize("cin,cout", [(16, 1), (16, 4), (16, 8), (16, 16), (16, 32), (4, 8), (4, 4)])
+@pytest.mark.parametrize("cin,cout", [(16, 1), (16, 4), (16, 8), (16, 16), (16, 32), (4, 8), (4, 4), (8, 8), (8, 16)])
 def test_conv_k3_octet_h2_vs_oracle(cin, cout):
     """full-octet h2 kernels (halo of h2 rows in shared memory, parent's map) == oracle on the 8-child expansion;
     cin = 4: all three split products in one MMA."""
