@@ -52,6 +52,7 @@ struct OctetH2Tune {
     // smaller row groups that leaves room for -- measured SLOWER on B200 (profiles/r01_h2_sweep.txt: 16x16 0.301 ms vs
     // 0.370 / 0.400; 16x4 0.217 vs 0.311 / 0.238), i.e. the halo latency is already hidden by the other warps and the
     // extra weight reads cost more; kept selectable for the next round's CTA-shared halo work.
+    // (12 instead of 8 warps for the narrow-output CIN = 16 kernels: 168 registers, spills, 0.262 vs 0.224 ms -- l1tex bound, not latency bound)
     static constexpr bool DB = V != 0;
     static constexpr int RG = DB ? (NT ? 1 : 2) : (NT ? 2 : (COUT == 16 ? 4 : 2));
     static constexpr int WARPS = DB ? (V == 1 ? 10 : 8) : (NT ? (CIN == 8 ? 16 : 8) : (COUT == 16 ? (CIN == 8 ? 12 : 8) : 16));
@@ -135,7 +136,8 @@ static int launch_octet_h2c4(const uint32_t *in, int in_ld, const int32_t *pnbr,
 static bool octet_h2c4_shape(int cin, int cout) { return cin == 4 && (cout == 4 || cout == 8); }
 static bool octet_h2_shape(int cin, int cout) {
     return (cin == 16 && (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32)) || (cin == 8 && (cout == 8 || cout == 16)) ||
-           octet_h2c4_shape(cin, cout);
+           octet_h2c4_shape(cin, cout);       // (cin = 32 was measured at the 435 k-row level: 0.142 / 0.313 ms for 32x8 / 32x32 against
+                                              // 0.119 / 0.217 ms of the gather kernels -- 8 KB halos leave 6-10 warps per SM; not instantiated)
 }
 
 // k=2 stride-2 convolution = the gather kernel over the 8 child slots of every parent (KV = 8, T formulation)
