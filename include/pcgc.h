@@ -267,6 +267,9 @@ enum { PCGC_ROUTE_H2_GATHER = 0, PCGC_ROUTE_H2_OCTET = 1, PCGC_ROUTE_TF32_GATHER
 /* PCGC_IRN_FUSED_TAIL: conv1_1 (k=3) and conv1_2 (k=1) run as one kernel (pcgc_conv_k3_octet_h2_k1_fwd); route[2] must be
  * PCGC_ROUTE_H2_OCTET and the shape supported. */
 #define PCGC_IRN_FUSED_TAIL 2
+/* PCGC_IRN_DUAL_SECOND (with PCGC_IRN_MERGED_FIRST, c = 16, routes 1 and 2 PCGC_ROUTE_H2_OCTET): conv0_1 and conv1_1 + conv1_2
+ * run as one kernel (pcgc_irn16_second_stage_fwd): the block is two launches. */
+#define PCGC_IRN_DUAL_SECOND 4
 typedef struct pcgc_irn_args {
     int64_t n;                      /* rows of the coordinate set */
     int32_t c;                      /* block channels (16, 32, 64) */
@@ -431,6 +434,18 @@ int pcgc_conv_k3_octet_h2_k1_fwd(const uint32_t *in_h2, int32_t in_ld, const int
                                  const uint32_t *packed, float inv_scale, const float *bias, int32_t cin, int32_t cmid,
                                  const float *tail_weight, const float *tail_bias, int32_t cout, const float *residual, int32_t res_ld,
                                  float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t *overflow, void *stream);
+
+/* Second stage of a 16-channel InceptionResNet block in ONE kernel (autoencoder.py:52-57 with channels = 16):
+ *     out[:, 0:8]  = conv0_1(a) + x[:, 0:8]                       (k=3, 4 -> 8)
+ *     out[:, 8:16] = conv1_2(relu(conv1_1(b))) + x[:, 8:16]      (k=3, 4 -> 4, then k=1, 4 -> 8)
+ * ab_h2 [8 n_parents][>= 8 words]: a | b, the h2 rows the merged first stage wrote (PCGC_IRN_MERGED_FIRST); every 32-byte row is
+ * staged once into two CIN = 4 halos.  packed01 / packed11: pcgc_conv_k3_h2_pack_weights of the 4 -> 8 / 4 -> 4 kernels;
+ * weight12 fp32 [4][8]; x / out fp32 [n][16] (the block input and output), out_h2 the h2 copy of out (either output may be NULL). */
+int pcgc_irn16_second_stage_fwd(const uint32_t *ab_h2, int32_t ab_ld, const int32_t *parent_nbr, int64_t n_parents,
+                                const uint32_t *packed01, float inv_scale01, const float *bias01, const uint32_t *packed11,
+                                float inv_scale11, const float *bias11, const float *weight12, const float *bias12, const float *x,
+                                int32_t x_ld, float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t *overflow,
+                                void *stream);
 
 /* ---- occupancy loss of the training path (row f4) ----------------------------------------------
  * get_bce(data, ground_truth) -- loss.py:7-15 (trainer.py:127-130): isin(data.C, ground_truth.C)

@@ -96,7 +96,7 @@ class Codec:
     WIDE_SHAPES = {(64, 64)}            # (cin, cout) of the k=3 layers routed to the tcgen05 / TMA kernel
 
     def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True, use_h2=True, fuse_irn=True,
-                 coords_coder="octree", wide_shapes=None, merge_first=True, coord_bits=None, fuse_tail=True):
+                 coords_coder="octree", wide_shapes=None, merge_first=True, coord_bits=None, fuse_tail=True, dual_second=True):
         """``coords_coder``: "octree" (in-process, default), None (hand the coordinates over raw, no ``Stream.C``) or any
         object with ``encode(int32 [n,3]) -> bytes`` / ``decode(bytes) -> int32 [n,3]`` (e.g. ``Tmc3CoordinateCoder``)."""
         # ``coord_bits``: the caller's promise that every input coordinate is below 2^coord_bits (coder.py's --res: 10 for vox10).
@@ -104,6 +104,7 @@ class Codec:
         # flag that is read with the pass's synchronising read, and the frame is coded again at full width (coord_bits_fallbacks).
         self.coord_bits = None if coord_bits is None else max(4, min(19, int(coord_bits)))
         self.coord_bits_fallbacks = 0
+        self.dual_second = dual_second      # ... and conv0_1 with them: a 16-channel block is two launches (needs merge_first, fuse_tail)
         self.fuse_tail = fuse_tail          # conv1_1 (k=3) + ReLU + conv1_2 (k=1) of the 16-channel blocks in one kernel
         self.merge_first = merge_first      # conv0_0 + conv1_0 of the 16-channel blocks as one k=3 convolution (see _merged_first)
         self.coords_coder = OctreeCoordinateCoder() if coords_coder == "octree" else coords_coder
@@ -354,6 +355,9 @@ class Codec:
             if (self.fuse_tail and self._h2_on and args.route[2] == _lib.ROUTE_H2_OCTET and
                     _lib.lib().pcgc_conv_k3_octet_h2_k1_supported(q, q, 2 * q)):
                 args.reserved |= 2                                    # PCGC_IRN_FUSED_TAIL: conv1_1 + ReLU + conv1_2 in one kernel
+                if (self.dual_second and (args.reserved & 1) and args.route[1] == _lib.ROUTE_H2_OCTET and
+                        int(self.w[prefix + ".conv0_0.kernel"].shape[1]) == 16):
+                    args.reserved |= 4                                # PCGC_IRN_DUAL_SECOND: conv0_1 and conv1_1 + conv1_2 in one kernel
             for i, leaf in enumerate((".conv1_0", ".conv1_2")):
                 args.w1[i], args.b1[i] = self.w[prefix + leaf + ".kernel"].data_ptr(), self.w[prefix + leaf + ".bias"].data_ptr()
             routes = list(args.route)

@@ -133,6 +133,28 @@ static int launch_octet_h2c4(const uint32_t *in, int in_ld, const int32_t *pnbr,
     return check_launch("conv_k3_octet_h2c4");
 }
 
+template <int RG, int WARPS, int MINB>
+static int launch_octet_h2c4_dual(const uint32_t *in, int in_ld, const int32_t *pnbr, int64_t n_par, const uint32_t *packed_a, float inv_a,
+                                  const float *bias_a, const uint32_t *packed_b, float inv_b, const float *bias_b, const float *tail_w,
+                                  const float *tail_b, const float *res, int res_ld, float *out, int out_ld, uint32_t *out_h2,
+                                  int out_h2_ld, int *overflow, cudaStream_t s) {
+    using C = OctetH2C4DualCfg<RG, WARPS>;
+    static_assert(C::smem_bytes() <= 227 * 1024, "dual octet h2c4 kernel: shared memory budget");
+    auto kern = conv_k3_octet_h2c4_dual_kernel<RG, WARPS, MINB>;
+    static int ctas = 0;
+    if (ctas == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes());
+        if (e != cudaSuccess) { set_error("dual octet h2c4 conv: %s", cudaGetErrorString(e)); return PCGC_ERR_CUDA; }
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, C::smem_bytes()) != cudaSuccess || nb < 1) nb = 1;
+        ctas = nb;
+    }
+    kern<<<grid_for(n_par, C::OCTETS_PER_CTA, ctas), C::THREADS, C::smem_bytes(), s>>>(in, in_ld, pnbr, n_par, packed_a, inv_a, bias_a, packed_b,
+                                                                                     inv_b, bias_b, tail_w, tail_b, res, res_ld, out, out_ld,
+                                                                                     out_h2, out_h2_ld, octet_tile_flag(), overflow);
+    return check_launch("conv_k3_octet_h2c4_dual");
+}
+
 static bool octet_h2c4_shape(int cin, int cout) { return cin == 4 && (cout == 4 || cout == 8); }
 static bool octet_h2_shape(int cin, int cout) {
     return (cin == 16 && (cout == 1 || cout == 4 || cout == 8 || cout == 16 || cout == 32)) || (cin == 8 && (cout == 8 || cout == 16)) ||
@@ -347,6 +369,23 @@ int pcgc_convT_k2s2_h2_fwd(const uint32_t *in_h2, int32_t in_ld, int64_t n_in, c
 }
 
 int pcgc_conv_k3_octet_h2_supported(int32_t cin, int32_t cout) { return octet_h2_shape(cin, cout) ? 1 : 0; }
+
+int pcgc_irn16_second_stage_fwd(const uint32_t *ab_h2, int32_t ab_ld, const int32_t *parent_nbr, int64_t n_parents,
+                                const uint32_t *packed01, float inv_scale01, const float *bias01, const uint32_t *packed11,
+                                float inv_scale11, const float *bias11, const float *weight12, const float *bias12, const float *x,
+                                int32_t x_ld, float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t *overflow,
+                                void *stream) {
+    PCGC_REQUIRE(n_parents >= 0 && 8 * n_parents < 0x7FFFFFFF && ab_ld >= 8, "pcgc_irn16_second_stage_fwd: bad shape");
+    if (n_parents == 0) return PCGC_OK;
+    PCGC_REQUIRE(ab_h2 && parent_nbr && packed01 && packed11 && weight12 && x && (out || out_h2), "pcgc_irn16_second_stage_fwd: null pointer");
+    PCGC_REQUIRE((ab_ld % 4 == 0) && (((uintptr_t)ab_h2 & 15) == 0), "pcgc_irn16_second_stage_fwd: input rows must be 16-byte aligned");
+    PCGC_REQUIRE(x_ld >= 16 && x_ld % 2 == 0 && ((uintptr_t)x & 7) == 0, "pcgc_irn16_second_stage_fwd: x must be 8-byte aligned [n][16]");
+    PCGC_REQUIRE(!out || (out_ld >= 16 && out_ld % 2 == 0 && ((uintptr_t)out & 7) == 0), "pcgc_irn16_second_stage_fwd: out must be 8-byte aligned");
+    PCGC_REQUIRE(!out_h2 || (out_h2_ld >= 16 && out_h2_ld % 4 == 0 && ((uintptr_t)out_h2 & 15) == 0),
+                 "pcgc_irn16_second_stage_fwd: h2 output rows must be 16-byte aligned");
+    return launch_octet_h2c4_dual<2, 8, 2>(ab_h2, ab_ld, parent_nbr, n_parents, packed01, inv_scale01, bias01, packed11, inv_scale11, bias11,
+                                           weight12, bias12, x, x_ld, out, out_ld, out_h2, out_h2_ld, overflow, (cudaStream_t)stream);
+}
 
 int pcgc_conv_k3_octet_h2_k1_supported(int32_t cin, int32_t cmid, int32_t cout) { return cin == 4 && cmid == 4 && cout == 8 ? 1 : 0; }
 

@@ -53,7 +53,10 @@ __host__ __device__ __forceinline__ constexpr int halo_child(int h) { return (h 
 // (compile-time, fully unrolled) iteration -- so the parent neighbour index q, the child bits cc and both
 // addresses are "lane constant + immediate" and a piece costs LDS (parent row) + max + compare + one
 // 32x32->64 multiply-add + LDGSTS.
-template <int PPR, int OW, int HB, int ROWB, int SY, int SZ, bool SWZ>
+// PIECE_STRIDE: byte distance between the destinations of consecutive 16-byte pieces of a row (16 = the row is stored whole;
+// a plane size = every piece goes to its own copy of the halo layout: the two 4-channel halves of an 8-channel row feed two
+// independent CIN = 4 halos, conv_k3_octet_h2c4_dual_kernel)
+template <int PPR, int OW, int HB, int ROWB, int SY, int SZ, bool SWZ, int PIECE_STRIDE = 16>
 __device__ __forceinline__ void halo_fill_plane(int hz, unsigned char *halo, const int32_t *sidx, const char *in_bytes,
                                                 uint32_t ldb, int lane) {
     constexpr int LPI = 32 / PPR;                                   // halo positions per warp instruction
@@ -70,17 +73,17 @@ __device__ __forceinline__ void halo_fill_plane(int hz, unsigned char *halo, con
         const int cc = halo_child(hx) | (halo_child(hy) << 1) | (halo_child(hz) << 2);
         const int32_t p = sidx[q * OW + o];
         const int piece = SWZ ? ((((j >> 2) ^ (hx & 1)) << 2) | (j & 3)) : j;
-        unsigned char *dst = halo + o * HB + (hx + SY * hy + SZ * hz) * ROWB + piece * 16;
+        unsigned char *dst = halo + o * HB + (hx + SY * hy + SZ * hz) * ROWB + piece * PIECE_STRIDE;
         const char *src = in_bytes + (size_t)cc * ldb + 16 * j + (uint64_t)(uint32_t)max(p, 0) * stride8;
         cp_async16_ca(dst, src, p >= 0);
     }
 }
-template <int PPR, int OW, int HB, int ROWB, int SY, int SZ, bool SWZ>
+template <int PPR, int OW, int HB, int ROWB, int SY, int SZ, bool SWZ, int PIECE_STRIDE = 16>
 __device__ __forceinline__ void halo_fill(unsigned char *halo, const int32_t *sidx, const char *in_bytes, uint32_t ldb,
                                           int lane) {
 #pragma unroll
     for (int hz = 0; hz < 4; ++hz) {
-        halo_fill_plane<PPR, OW, HB, ROWB, SY, SZ, SWZ>(hz, halo, sidx, in_bytes, ldb, lane);
+        halo_fill_plane<PPR, OW, HB, ROWB, SY, SZ, SWZ, PIECE_STRIDE>(hz, halo, sidx, in_bytes, ldb, lane);
         cp_async_commit();                                          // group hz
     }
 }

@@ -436,4 +436,130 @@ conv_k3_octet_h2c4_kernel(const uint32_t *__restrict__ in, int in_ld, const int3
     if (epi.over && overflow) *overflow = 1;
 }
 
+// ---- both second-stage layers of a 16-channel InceptionResNet block in one kernel --------------------------------------
+// conv0_1 (k=3, 4 -> 8, + x[:, :8]) reads a, conv1_1 (k=3, 4 -> 4, ReLU) -> conv1_2 (k=1, 4 -> 8, + x[:, 8:]) reads b, and a | b are
+// the two 16-byte halves of the rows the merged first layer wrote (PCGC_IRN_MERGED_FIRST).  One pass stages every 32-byte row
+// ONCE (one sector; the two single-branch kernels each fetched the same sector for their half) into two CIN = 4 halo planes
+// and runs both MMA chains on them; the block's 16 output channels leave from one epilogue.  Arithmetic per branch is that of
+// conv_k3_octet_h2c4_kernel (<8> and <4, K1TAIL>), bit for bit.
+template <int RG_, int WARPS_>
+struct OctetH2C4DualCfg {
+    using A = OctetH2C4Cfg<8, RG_, WARPS_>;
+    static constexpr int RG = RG_, WARPS = WARPS_, THREADS = 32 * WARPS_, OW = 2 * RG_;
+    static constexpr int SY = A::SY, SZ = A::SZ, HB = A::HB, W_OFF = 64;
+    static constexpr int PLANE = OW * HB;                          // bytes of one branch's halos of a warp
+    static constexpr size_t weight_bytes() { return ((size_t)2 * 27 * W_OFF * 4 + 127) / 128 * 128; }
+    static constexpr size_t warp_bytes() { return ((size_t)2 * PLANE + (size_t)27 * OW * 4 + 127) / 128 * 128; }
+    static constexpr size_t smem_bytes() { return weight_bytes() + (size_t)WARPS * warp_bytes(); }
+    static constexpr int OCTETS_PER_CTA = WARPS * OW;
+};
+
+template <int RG, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+conv_k3_octet_h2c4_dual_kernel(const uint32_t *__restrict__ in, int in_ld, const int32_t *__restrict__ pnbr, int64_t n_par,
+                               const uint32_t *__restrict__ packed_a, float inv_scale_a, const float *__restrict__ bias_a,
+                               const uint32_t *__restrict__ packed_b, float inv_scale_b, const float *__restrict__ bias_b,
+                               const float *__restrict__ tail_w, const float *__restrict__ tail_b,
+                               const float *__restrict__ residual, int res_ld, float *__restrict__ out, int out_ld,
+                               uint32_t *__restrict__ out_h2, int out_h2_ld, int flags, int *__restrict__ overflow) {
+    using C = OctetH2C4DualCfg<RG, WARPS>;
+    constexpr int OW = C::OW, SY = C::SY, SZ = C::SZ, HB = C::HB, W_OFF = C::W_OFF, PLANE = C::PLANE;
+    extern __shared__ __align__(128) unsigned char smem_oh2[];
+    uint32_t *wsm_a = reinterpret_cast<uint32_t *>(smem_oh2), *wsm_b = wsm_a + 27 * W_OFF;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    unsigned char *halo = smem_oh2 + C::weight_bytes() + (size_t)warp * C::warp_bytes();
+    int32_t *sidx = reinterpret_cast<int32_t *>(halo + (size_t)2 * PLANE);
+
+    for (int i = threadIdx.x; i < 27 * W_OFF; i += C::THREADS) { wsm_a[i] = __ldg(packed_a + i); wsm_b[i] = __ldg(packed_b + i); }
+    __syncthreads();
+
+    const int cx = g & 1, cy = (g >> 1) & 1, cz = g >> 2;
+    const unsigned char *base = halo + (cx + SY * cy + SZ * cz) * 16 + 4 * t;       // child g, word t of the a row; b: + PLANE
+    const bool dup = t < 2;
+
+    const int64_t n_tiles = (n_par + C::OCTETS_PER_CTA - 1) / C::OCTETS_PER_CTA;
+    const char *in_bytes = reinterpret_cast<const char *>(in);
+    const uint32_t ldb = (uint32_t)in_ld * 4u;
+    // output channels 0..7 (branch a) and 8..15 (branch b: the k=1 tail) of the block's rows
+    H2Epilogue epi_a{bias_a, residual, out, out_h2, res_ld, out_ld, out_h2_ld, 0, inv_scale_a};
+    H2Epilogue epi_b{tail_b, residual ? residual + 8 : nullptr, out ? out + 8 : nullptr, out_h2 ? out_h2 + 8 : nullptr, res_ld, out_ld,
+                     out_h2_ld, 0, 1.f};
+    float tw[4][2], b0 = 0.f, b1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { tw[i][0] = __ldg(tail_w + i * 8 + 2 * t); tw[i][1] = __ldg(tail_w + i * 8 + 2 * t + 1); }
+    if (t < 2 && bias_b) { b0 = __ldg(bias_b + 2 * t); b1 = __ldg(bias_b + 2 * t + 1); }
+
+    int32_t prow[OW];
+    const bool chunked = flags & PCGC_TILES_CHUNKED;
+    const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t tile_begin = chunked ? blockIdx.x * per_cta : blockIdx.x, tile_step = chunked ? 1 : gridDim.x;
+    const int64_t tile_end = chunked ? min(n_tiles, tile_begin + per_cta) : n_tiles;
+    load_parent_rows<OW>(prow, pnbr, n_par, tile_begin * C::OCTETS_PER_CTA + warp * OW, lane);
+    for (int64_t tile = tile_begin; tile < tile_end; tile += tile_step) {
+        const int64_t oct0 = tile * C::OCTETS_PER_CTA + warp * OW;
+        __syncwarp();
+        store_parent_rows<OW>(sidx, prow, lane);
+        __syncwarp();
+        halo_fill<2, OW, HB, 16, SY, SZ, false, PLANE>(halo, sidx, in_bytes, ldb, lane);   // piece 0 -> plane a, piece 1 -> plane b
+        load_parent_rows<OW>(prow, pnbr, n_par, (tile + tile_step) * C::OCTETS_PER_CTA + warp * OW, lane);
+
+        float acc_a[RG][4], acc_b[RG][4];
+#pragma unroll
+        for (int r = 0; r < RG; ++r)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc_a[r][e] = acc_b[r][e] = 0.f;
+
+#pragma unroll
+        for (int iz = 0; iz < 3; ++iz) {
+            halo_wait(iz);
+            float pl_a[RG][4], pl_b[RG][4];
+#pragma unroll
+            for (int oo = 0; oo < 9; ++oo) {
+                const int o = 9 * iz + oo, ix = oo % 3, iy = oo / 3;
+                const int doff = (ix + SY * iy + SZ * iz) * 16;
+                const uint2 wa = *reinterpret_cast<const uint2 *>(wsm_a + o * W_OFF + lane * 2);
+                const uint2 wb = *reinterpret_cast<const uint2 *>(wsm_b + o * W_OFF + lane * 2);
+#pragma unroll
+                for (int r = 0; r < RG; ++r) {
+                    const uint32_t a0 = *reinterpret_cast<const uint32_t *>(base + (2 * r) * HB + doff);
+                    const uint32_t a1 = *reinterpret_cast<const uint32_t *>(base + (2 * r + 1) * HB + doff);
+                    const uint32_t c0 = *reinterpret_cast<const uint32_t *>(base + PLANE + (2 * r) * HB + doff);
+                    const uint32_t c1 = *reinterpret_cast<const uint32_t *>(base + PLANE + (2 * r + 1) * HB + doff);
+                    if (oo == 0) {
+                        mma_f16_zero(pl_a[r], a0, a1, dup ? a0 : 0u, dup ? a1 : 0u, wa.x, wa.y);
+                        mma_f16_zero(pl_b[r], c0, c1, dup ? c0 : 0u, dup ? c1 : 0u, wb.x, wb.y);
+                    } else {
+                        mma_f16(pl_a[r], a0, a1, dup ? a0 : 0u, dup ? a1 : 0u, wa.x, wa.y);
+                        mma_f16(pl_b[r], c0, c1, dup ? c0 : 0u, dup ? c1 : 0u, wb.x, wb.y);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RG; ++r)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { acc_a[r][e] += pl_a[r][e]; acc_b[r][e] += pl_b[r][e]; }
+        }
+
+        const int64_t n = n_par * 8, row0 = oct0 * 8;
+#pragma unroll
+        for (int r = 0; r < RG; ++r)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float v0 = fmaxf(acc_b[r][2 * h] * inv_scale_b + b0, 0.f), v1 = fmaxf(acc_b[r][2 * h + 1] * inv_scale_b + b1, 0.f);
+                const int q0 = lane & ~3;
+                const float c0 = __shfl_sync(0xffffffffu, v0, q0), c1 = __shfl_sync(0xffffffffu, v1, q0);
+                const float c2 = __shfl_sync(0xffffffffu, v0, q0 + 1), c3 = __shfl_sync(0xffffffffu, v1, q0 + 1);
+                const int64_t row = row0 + 16 * r + 8 * h + g;
+                if (row >= n) continue;
+                epi_a.store_pair(row, 2 * t, acc_a[r][2 * h], acc_a[r][2 * h + 1]);          // conv0_1 + bias + x[:, :8]
+                float y0 = c0 * tw[0][0], y1 = c0 * tw[0][1];
+                y0 = fmaf(c1, tw[1][0], y0); y1 = fmaf(c1, tw[1][1], y1);
+                y0 = fmaf(c2, tw[2][0], y0); y1 = fmaf(c2, tw[2][1], y1);
+                y0 = fmaf(c3, tw[3][0], y0); y1 = fmaf(c3, tw[3][1], y1);
+                epi_b.store_pair(row, 2 * t, y0, y1);                                        // conv1_2 + bias + x[:, 8:]
+            }
+    }
+    if ((epi_a.over || epi_b.over) && overflow) *overflow = 1;
+}
+
 }  // namespace pcgc

@@ -105,6 +105,16 @@ int pcgc_irn_fwd(const pcgc_irn_args *a, void *stream) {
         b_h = ab_h + q;
     }
 
+    if (a->reserved & PCGC_IRN_DUAL_SECOND) {                     // both second-stage branches in one kernel: two launches per block
+        if (!merged || c != 16 || a->route[1] != PCGC_ROUTE_H2_OCTET || a->route[2] != PCGC_ROUTE_H2_OCTET) {
+            pcgc::set_error("pcgc_irn_fwd: dual second stage needs merged first layers, c = 16 and the full-octet h2 routes");
+            return PCGC_ERR_INVALID;
+        }
+        return pcgc_irn16_second_stage_fwd(ab_h, ab_ld, a->parent_nbr, a->n / 8, (const uint32_t *)a->w3[1], a->inv_scale[1], a->b3[1],
+                                           (const uint32_t *)a->w3[2], a->inv_scale[2], a->b3[2], a->w1[1], a->b1[1], a->x, a->x_ld, a->out,
+                                           a->out_ld, a->out_h2, a->out_h2_ld, a->overflow, stream);
+    }
+
     // ---- branch 0: conv0_0 (c -> q, ReLU), conv0_1 (q -> h, + x[:, :h])
     const bool a_needs_h2 = h2_route(a->route[1]), a_needs_f32 = !a_needs_h2;
     if (merged) {

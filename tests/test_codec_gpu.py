@@ -247,18 +247,19 @@ def test_tcgen05_routes_give_the_same_stream_and_occupancy(r3):
     assert plain.encode(pts).F == a.F and (canon(plain.decode(a)) == canon(da)).all()
 
 
-@pytest.mark.parametrize("merge_first,fuse_tail", [(True, False), (False, True), (True, True)])
-def test_merged_first_layers_of_the_16_channel_blocks(r3, merge_first, fuse_tail):
+@pytest.mark.parametrize("merge_first,fuse_tail,dual", [(True, False, False), (False, True, False), (True, True, False), (True, True, True)])
+def test_merged_first_layers_of_the_16_channel_blocks(r3, merge_first, fuse_tail, dual):
     """conv0_0 (k=3) + conv1_0 (k=1) of the finest decoder blocks as ONE k=3 convolution 16 -> 8 (conv1_0's weights at the
     centre offset, PCGC_IRN_MERGED_FIRST) and conv1_1 (k=3) + ReLU + conv1_2 (k=1) as one kernel (PCGC_IRN_FUSED_TAIL): the
     block output stays within the h2 tolerance of the layer-by-layer block, the stream is untouched (the analysis network has
     no 16-channel block) and the decoded set is the same on the KAT cloud."""
     pts = synth.ellipsoid_vox8()
-    merged, plain = Codec(r3, merge_first=merge_first, fuse_tail=fuse_tail), Codec(r3, merge_first=False, fuse_tail=False)
+    merged = Codec(r3, merge_first=merge_first, fuse_tail=fuse_tail, dual_second=dual)
+    plain = Codec(r3, merge_first=False, fuse_tail=False)
     a, b = merged.encode(pts), plain.encode(pts)
     assert a.F == b.F and a.H == b.H and (a.coords == b.coords).all()
     da, db = merged.decode(a), plain.decode(b)
-    assert any(p["args"].reserved == (1 if merge_first else 0) + (2 if fuse_tail else 0) for p in merged._irn_plans.values())
+    assert any(p["args"].reserved == (1 if merge_first else 0) + (2 if fuse_tail else 0) + (4 if dual else 0) for p in merged._irn_plans.values())
     assert not any(p["args"].reserved for p in plain._irn_plans.values())
     assert (canon(da) == canon(db)).all()
     # one block in isolation on random features over the finest decoder set of the KAT cloud
