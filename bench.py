@@ -9,8 +9,8 @@ One "step" = ``--depth`` (default 4) point-cloud frames per GPU, each through on
 checkpoint, rho = 1), kept in flight together by ``pcgcv2_b200.pipeline.FramePipeline`` (one host thread +
 CUDA stream per frame, so the sequential host range coder of one frame overlaps the kernels of the
 other); ``config.serial_ms_per_frame`` is the one-frame-at-a-time latency measured in the same run.  With N
-ranks every rank codes its own frames (seed = rank, radii jittered +-10 %: config 3) -- the path is
-embarrassingly per-cloud, so the only collective is an all-gather of per-rank counters.
+ranks every rank codes the same workload (weak scaling; ``--config3-frames`` switches to config 3's four jittered
+clouds) -- the path is embarrassingly per-cloud, so the only collective is an all-gather of per-rank counters.
 
 Prints ONE JSON line (rank 0).  ``value`` = Mpoints/s with the input voxels already resident in
 HBM; ``e2e`` = the same through the public API with HOST buffers (pinned int32 coordinates in,
@@ -196,12 +196,13 @@ def run_ours(args, rank, world, local_rank):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
-    # N = 1: BASELINE config 2's stand-in, synthetic_vox10(0), 795 124 voxels, in every slot.  N > 1: config 3's four jittered
-    # clouds (seeds 0-3, radii +-10 %: 690-840 k voxels); the `depth` frames a rank keeps in flight are clouds (rank + j) mod 4,
-    # so with the default depth of 4 every rank codes all four clouds each step (rotated) and the ranks carry equal work --
-    # round 1 gave rank r cloud r only, and the max-over-ranks time then measured the largest cloud, not the scaling.
-    # --same-frames gives every slot of every rank seed 0's unjittered cloud.
+    # Every slot of every rank codes BASELINE config 2's stand-in, synthetic_vox10(0), 795 124 voxels: per-GPU work is the same
+    # at every N (weak scaling), and config 3's four distinct clouds are parity-test cases (tests/test_fullsize_gpu.py).
+    # --config3-frames: the four jittered clouds instead (seeds 0-3, radii +-10 %: 690-840 k voxels); the `depth` frames a rank
+    # keeps in flight are clouds (rank + j) mod 4, so with depth 4 every rank codes all four each step and the ranks still
+    # carry equal work (round 1 gave rank r cloud r only: the max-over-ranks time then measured the largest cloud).
     depth = max(1, args.depth)
+    args.same_frames = not args.config3_frames
     if world > 1 and not args.same_frames:
         clouds = [synth.synthetic_vox10(seed=s, jitter=0.1) for s in range(4)]
         frames_np = [clouds[(rank + j) % 4] for j in range(depth)]
@@ -449,7 +450,8 @@ def main():
     ap.add_argument("--workload", default="codec", choices=["codec", "train"],
                     help="codec = BASELINE's headline (default); train = the config-5 training step (tools/bench_train.py)")
     ap.add_argument("--batch", type=int, default=32, help="--workload train: samples per rank and step")
-    ap.add_argument("--same-frames", action="store_true", help="every rank codes rank 0's cloud (no frame-size variance between ranks)")
+    ap.add_argument("--config3-frames", action="store_true",
+                    help="N > 1: code config 3's four jittered clouds (every rank all four, rotated) instead of config 2's cloud in every slot")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
