@@ -13,6 +13,8 @@
 
 namespace pcgc {
 
+constexpr int kWgradTileRows = 64;
+
 enum PairMode { PAIR_K3 = 0, PAIR_IDENT = 1, PAIR_DOWN = 2, PAIR_UP = 3 };
 
 // one (blockIdx.y = k) x (chunk of rows): gw[k][ca][cb] += sum_rows A[ia]^T (x) B[ib]
@@ -26,8 +28,8 @@ weight_grad_kernel(int mode, const float *__restrict__ A, int a_ld, const float 
                    const int32_t *__restrict__ nbr, const int32_t *__restrict__ parent_of,
                    const uint64_t *__restrict__ keys, int64_t n, int ca, int cb, int rows_per_block,
                    float *__restrict__ partial) {
-    constexpr int TR = 16;
-    extern __shared__ float sm[];
+    constexpr int TR = kWgradTileRows;     // rows per shared-memory tile: 64 FMAs per element between two barriers (16 left the
+    extern __shared__ float sm[];          // kernel barrier-bound: 64 of the 94 ms of GPU time of a config-5 training step)
     float *as = sm;                    // [TR][ca]
     float *bs = sm + TR * ca;          // [TR][cb]
     __shared__ int64_t ia_s[TR], ib_s[TR];
@@ -67,7 +69,7 @@ weight_grad_kernel(int mode, const float *__restrict__ A, int a_ld, const float 
             if (idx < total) {
                 const int ci = idx / cb, co = idx % cb;
                 float s = 0.f;
-#pragma unroll
+#pragma unroll 16
                 for (int r = 0; r < TR; ++r) s = fmaf(as[r * ca + ci], bs[r * cb + co], s);
                 acc[e] += s;
             }
@@ -166,9 +168,13 @@ static int launch_weight_grad(int mode, const float *A, int a_ld, const float *B
     const int rows_per_block = weight_grad_rows_per_block(n);
     dim3 grid((unsigned)((n + rows_per_block - 1) / rows_per_block), kvol);
     float *part = (float *)ws;
-    const size_t smem = sizeof(float) * 16 * (ca + cb);
+    const size_t smem = sizeof(float) * kWgradTileRows * (ca + cb);
     const int e = (ca * cb + 255) / 256;
-#define WG(E) weight_grad_kernel<E><<<grid, 256, smem, s>>>(mode, A, a_ld, B, b_ld, nbr, parent_of, keys, n, ca, cb, rows_per_block, part)
+#define WG(E)                                                                                                                          \
+    do {                                                                                                                               \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(weight_grad_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        weight_grad_kernel<E><<<grid, 256, smem, s>>>(mode, A, a_ld, B, b_ld, nbr, parent_of, keys, n, ca, cb, rows_per_block, part); \
+    } while (0)
     if (e <= 1) WG(1); else if (e <= 4) WG(4); else if (e <= 16) WG(16); else WG(64);
 #undef WG
     int rc = check_launch("weight_grad");
