@@ -83,6 +83,82 @@ weight_grad_kernel(int mode, const float *__restrict__ A, int a_ld, const float 
     }
 }
 
+// The same sums with register micro-tiles, for channel counts that are multiples of 4 with at most 256 micro-tiles (every layer
+// of the codec except the 1-channel ends): thread (m, sl) owns the 4 x 4 block m of gw[k] and the rows sl, sl + S, ... of each
+// shared-memory tile (S = 256 / micro-tiles row slices), i.e. two LDS.128 feed 16 FMAs (the element-per-thread kernel above
+// issues two LDS per FMA); the S slices are added in slice order through shared memory at the end -- deterministic like the rest.
+__global__ void __launch_bounds__(256)
+weight_grad_mt_kernel(int mode, const float *__restrict__ A, int a_ld, const float *__restrict__ B, int b_ld,
+                      const int32_t *__restrict__ nbr, const int32_t *__restrict__ parent_of, const uint64_t *__restrict__ keys,
+                      int64_t n, int ca, int cb, int rows_per_block, float *__restrict__ partial) {
+    constexpr int TR = kWgradTileRows;
+    extern __shared__ __align__(16) float sm[];
+    float *as = sm;                    // [TR][ca]
+    float *bs = sm + TR * ca;          // [TR][cb]
+    __shared__ int64_t ia_s[TR], ib_s[TR];
+    const int k = blockIdx.y, total = ca * cb;
+    const int nbj = cb >> 2, nm = (ca >> 2) * nbj, S = 256 / nm;
+    const int m = threadIdx.x % nm, sl = threadIdx.x / nm;
+    const int mi = m / nbj, mj = m % nbj;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min(n, r_begin + rows_per_block);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += TR) {
+        if (threadIdx.x < TR) {
+            const int64_t u = r0 + threadIdx.x;
+            int64_t ia = -1, ib = -1;
+            if (u < r_end) {
+                if (mode == PAIR_K3) { ia = nbr[(int64_t)k * n + u]; ib = u; }
+                else if (mode == PAIR_IDENT) { ia = u; ib = u; }
+                else if (mode == PAIR_DOWN) { if ((int)(keys[u] & 7) == k) { ia = u; ib = parent_of[u]; } }
+                else { ia = u; ib = 8 * u + k; }
+            }
+            ia_s[threadIdx.x] = ia;
+            ib_s[threadIdx.x] = ia < 0 ? -1 : ib;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < TR * ca; i += blockDim.x) {
+            const int r = i / ca, c = i % ca;
+            as[i] = ia_s[r] >= 0 ? A[ia_s[r] * a_ld + c] : 0.f;
+        }
+        for (int i = threadIdx.x; i < TR * cb; i += blockDim.x) {
+            const int r = i / cb, c = i % cb;
+            bs[i] = ib_s[r] >= 0 ? B[ib_s[r] * b_ld + c] : 0.f;
+        }
+        __syncthreads();
+        if (sl < S) {
+            for (int r = sl; r < TR; r += S) {
+                const float4 a = *reinterpret_cast<const float4 *>(as + r * ca + 4 * mi);
+                const float4 b = *reinterpret_cast<const float4 *>(bs + r * cb + 4 * mj);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+    // slice sums -> shared memory [S][total] (element ci * cb + co), then added in slice order
+    float *red = sm;
+    if (sl < S) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[(size_t)sl * total + (4 * mi + i) * cb + 4 * mj + j] = acc[i][j];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        float sum = 0.f;
+        for (int q = 0; q < S; ++q) sum += red[(size_t)q * total + idx];
+        partial[((int64_t)blockIdx.x * gridDim.y + k) * total + idx] = sum;
+    }
+}
+
 // out[i] = partial[0][i] + partial[1][i] + ... in block order
 __global__ void sum_partials_kernel(const float *__restrict__ partial, int blocks, int64_t count, float *__restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
@@ -168,6 +244,20 @@ static int launch_weight_grad(int mode, const float *A, int a_ld, const float *B
     const int rows_per_block = weight_grad_rows_per_block(n);
     dim3 grid((unsigned)((n + rows_per_block - 1) / rows_per_block), kvol);
     float *part = (float *)ws;
+    const int nm = (ca / 4) * (cb / 4);
+    if (ca % 4 == 0 && cb % 4 == 0 && nm >= 1 && nm <= 256) {     // register micro-tiles
+        const size_t tile = sizeof(float) * kWgradTileRows * (ca + cb), red = sizeof(float) * (size_t)(256 / nm) * ca * cb;
+        const size_t smem_mt = tile > red ? tile : red;
+        static bool opted = false;
+        if (!opted) { cudaFuncSetAttribute(weight_grad_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); opted = true; }
+        PCGC_REQUIRE(smem_mt <= 96 * 1024, "weight gradient: %dx%d channels need too much shared memory", ca, cb);
+        weight_grad_mt_kernel<<<grid, 256, smem_mt, s>>>(mode, A, a_ld, B, b_ld, nbr, parent_of, keys, n, ca, cb, rows_per_block, part);
+        int rc = check_launch("weight_grad_mt");
+        if (rc) return rc;
+        const int64_t count = (int64_t)kvol * ca * cb;
+        sum_partials_kernel<<<grid_for(count, 256, 4), 256, 0, s>>>(part, (int)grid.x, count, gw);
+        return check_launch("weight_grad_sum");
+    }
     const size_t smem = sizeof(float) * kWgradTileRows * (ca + cb);
     const int e = (ca * cb + 255) / 256;
 #define WG(E)                                                                                                                          \
