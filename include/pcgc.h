@@ -425,6 +425,15 @@ int pcgc_conv_k3_octet_tc05_fwd(const uint32_t *feats_h2, int32_t in_ld, const i
                                 const float *residual, int32_t res_ld, float *out, int32_t out_ld, uint32_t *out_h2,
                                 int32_t out_h2_ld, int32_t flags, int32_t *overflow, void *stream);
 
+/* a3 for the FIRST layer (encoder.conv0, autoencoder.py:71,138): the input features are the constant 1 of every voxel
+ * (data_utils.py:94, coder.py:131), so out[u] = bias + sum over PRESENT neighbours k of weight[k][0][:] -- computed from the
+ * PARENT set's kernel map and child-occupancy info (arguments as pcgc_kernel_map_k3_from_parent, non-full-octet mode) without
+ * ever building the 27 x n kernel map of the set.  cout = 16; out fp32 and / or out_h2 (either may be NULL). */
+int pcgc_conv_k3_ones_from_parent_fwd(const uint64_t *child_keys, const int32_t *parent_of, const uint64_t *parent_info,
+                                      const int32_t *parent_nbr, int64_t n_parents, int64_t n, const float *weight, const float *bias,
+                                      int32_t cout, float *out, int32_t out_ld, uint32_t *out_h2, int32_t out_h2_ld, int32_t flags,
+                                      int32_t *overflow, void *stream);
+
 /* k=3 convolution + ReLU + the k=1 convolution that follows it, in one kernel (conv1_1 -> conv1_2 of an InceptionResNet
  * block, autoencoder.py:28,42,55): out = relu(conv_k3(in; packed, bias)) @ tail_weight[cmid][cout] + tail_bias + residual.
  * The intermediate is never written.  Shapes: pcgc_conv_k3_octet_h2_k1_supported (4 -> 4 -> 8 today); arguments otherwise

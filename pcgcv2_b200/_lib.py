@@ -112,6 +112,8 @@ SIGNATURES = {
     "pcgc_rc_decode_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
     "pcgc_rc_encode_u16_host": (c_i64, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
     "pcgc_rc_decode_u16_host": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_i64, c_p, c_i64]),
+    "pcgc_conv_k3_ones_from_parent_fwd": (ctypes.c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_i32, c_p, c_i32, c_p, c_i32, c_i32,
+                                                         c_p, c_p]),
     "pcgc_irn16_second_stage_fwd": (ctypes.c_int, [c_p, c_i32, c_p, c_i64, c_p, ctypes.c_float, c_p, c_p, ctypes.c_float, c_p, c_p, c_p,
                                                    c_p, c_i32, c_p, c_i32, c_p, c_i32, c_p, c_p]),
     "pcgc_conv_k3_octet_h2_k1_supported": (ctypes.c_int, [c_i32, c_i32, c_i32]),

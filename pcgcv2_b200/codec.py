@@ -96,7 +96,7 @@ class Codec:
     WIDE_SHAPES = {(64, 64)}            # (cin, cout) of the k=3 layers routed to the tcgen05 / TMA kernel
 
     def __init__(self, state_dict, device="cuda", use_tensor_cores=True, use_octet_kernels=True, use_h2=True, fuse_irn=True,
-                 coords_coder="octree", wide_shapes=None, merge_first=True, coord_bits=None, fuse_tail=True, dual_second=True):
+                 coords_coder="octree", wide_shapes=None, merge_first=True, coord_bits=None, fuse_tail=True, dual_second=True, fuse_conv0=True):
         """``coords_coder``: "octree" (in-process, default), None (hand the coordinates over raw, no ``Stream.C``) or any
         object with ``encode(int32 [n,3]) -> bytes`` / ``decode(bytes) -> int32 [n,3]`` (e.g. ``Tmc3CoordinateCoder``)."""
         # ``coord_bits``: the caller's promise that every input coordinate is below 2^coord_bits (coder.py's --res: 10 for vox10).
@@ -105,6 +105,7 @@ class Codec:
         self.coord_bits = None if coord_bits is None else max(4, min(19, int(coord_bits)))
         self.coord_bits_fallbacks = 0
         self.dual_second = dual_second      # ... and conv0_1 with them: a 16-channel block is two launches (needs merge_first, fuse_tail)
+        self.fuse_conv0 = fuse_conv0        # encoder.conv0 on its constant-one input straight from the parent's kernel map
         self.fuse_tail = fuse_tail          # conv1_1 (k=3) + ReLU + conv1_2 (k=1) of the 16-channel blocks in one kernel
         self.merge_first = merge_first      # conv0_0 + conv1_0 of the 16-channel blocks as one k=3 convolution (see _merged_first)
         self.coords_coder = OctreeCoordinateCoder() if coords_coder == "octree" else coords_coder
@@ -449,8 +450,18 @@ class Codec:
             levels.append(_Level(pk, levels[-1].stride * 2))
         for child, par in zip(levels[:-1], levels[1:]):
             child.parent = par
-        x = _F(torch.ones((len(level0), 1), dtype=torch.float32, device=self.device))
-        x = self._k3("encoder.conv0", x, level0, relu=True)
+        w0 = self.w["encoder.conv0.kernel"]
+        if (self.fuse_conv0 and self.record is None and "encoder.conv0" not in self.probe and w0.shape[1] == 1 and w0.shape[2] == 16
+                and level0.info is not None):
+            # the input features are the constant 1 (coder.py:131): conv0 = bias + the sum of the weights of the PRESENT neighbours,
+            # read off the parent's kernel map -- the 27 x N0 kernel map of the finest level is never built
+            want_h = self._h2_on and "encoder.down0" in self.packed_down_h2
+            x = _F(*ops.conv_k3_ones_from_parent(level0.parent.nbr, level0.keys, level0.parent_of, level0.info, w0,
+                                                 self.w["encoder.conv0.bias"], relu=True, want_f32=not want_h, want_h2=want_h,
+                                                 overflow=self._overflow))
+        else:
+            x = _F(torch.ones((len(level0), 1), dtype=torch.float32, device=self.device))
+            x = self._k3("encoder.conv0", x, level0, relu=True)
         level, sizes = level0, [len(level0)]
         for i in range(3):
             rows, off = down[i]

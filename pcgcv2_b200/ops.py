@@ -187,6 +187,20 @@ def kernel_map_k3_from_parent(parent_nbr: torch.Tensor, n: int, child_keys=None,
     return nbr
 
 
+def conv_k3_ones_from_parent(parent_nbr, child_keys, parent_of, info, weight, bias, relu=True, want_f32=True, want_h2=False,
+                             overflow=None):
+    """encoder.conv0 on constant-one features straight from the parent's kernel map (no child map): weight [27, 1, 16]
+    -> (fp32 [n, 16] or None, h2 [n, 16] or None)."""
+    n, n_par, cout = child_keys.shape[0], parent_nbr.shape[1], weight.shape[2]
+    assert weight.shape[0] == 27 and weight.shape[1] == 1 and weight.is_contiguous()
+    out = torch.empty((n, cout), dtype=torch.float32, device=child_keys.device) if want_f32 else None
+    out_h2 = torch.empty((n, cout), dtype=torch.int32, device=child_keys.device) if want_h2 else None
+    check(_lib.lib().pcgc_conv_k3_ones_from_parent_fwd(_p(child_keys), _p(parent_of), _p(info), _p(parent_nbr), n_par, n, _p(weight),
+                                                       _p(bias), cout, _p(out), cout, _p(out_h2), cout, EPI_RELU if relu else 0,
+                                                       _p(overflow), _stream()), "pcgc_conv_k3_ones_from_parent_fwd")
+    return out, out_h2
+
+
 def upsample_keys(keys: torch.Tensor) -> torch.Tensor:
     n = keys.shape[0]
     out = torch.empty(8 * n, dtype=torch.int64, device=keys.device)

@@ -295,3 +295,13 @@ def test_coord_bits_hint_is_the_same_codec_and_falls_back(r3):
     d = hinted.encode(shifted)
     assert hinted.coord_bits_fallbacks == 1
     assert (canon(hinted.decode(d)) == canon(full.decode(full.encode(shifted)))).all()
+
+
+def test_fused_first_layer_gives_the_same_stream(r3):
+    """Codec(fuse_conv0=True) (encoder.conv0 from the parent's map, no finest-level kernel map) == the generic first layer:
+    same bitstream and decoded set on the KAT cloud and on a cube with duplicates removed."""
+    for pts in (synth.ellipsoid_vox8(), synth.random_cube(0, 32, 0.1)):
+        a, b = Codec(r3, fuse_conv0=True), Codec(r3, fuse_conv0=False)
+        sa, sb = a.encode(pts), b.encode(pts)
+        assert sa.F == sb.F and sa.H == sb.H and (sa.coords == sb.coords).all() and sa.num_points == sb.num_points
+        assert (canon(a.decode(sa)) == canon(b.decode(sb))).all()

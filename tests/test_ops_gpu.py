@@ -749,3 +749,27 @@ def test_symbol_ranges_on_the_device_code_the_same_stream():
     bad[7, 3] = lp - 1
     with pytest.raises(ValueError):
         ops.symbol_ranges(torch.from_numpy(bad).to(DEV), torch.from_numpy(tab.view(np.int16)).to(DEV))
+
+
+def test_first_layer_on_constant_one_features_from_the_parent_map():
+    """encoder.conv0 fused with its neighbourhood lookup (csrc/conv_ones.cu): out = relu(bias + sum of the weights of the present
+    neighbours), presence read off the PARENT's kernel map -- == the oracle's k=3 convolution of an all-ones feature column, in
+    fp32 and in the h2 copy; ragged sizes (warp tails), isolated voxels, a single voxel."""
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(27, 1, 16, generator=g) / np.sqrt(27)
+    b = torch.randn(1, 16, generator=g)
+    for n in (20011, 33, 32, 1):
+        c = _surface()[:n]
+        if n == 33:
+            c = np.concatenate([c, np.array([[0, 500, 3, 7], [0, 2, 900, 901]], dtype=c.dtype)])      # far-away singletons
+        keys, _ = ops.argsort_u64(_keys(c))
+        cs = ops.unpack_keys(keys, 1).cpu().numpy()
+        pk, rows, off, parent_of = ops.stride_down(keys, keys_are_sorted=True, with_parent_of=True)
+        info = ops.parent_info(keys, off)
+        pnbr = ops.kernel_map_k3(pk, ops.HashTable(pk))
+        flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+        got, got_h = ops.conv_k3_ones_from_parent(pnbr, keys, parent_of, info, w.to(DEV), b.to(DEV), relu=True, want_h2=True, overflow=flag)
+        ref = torch.relu(S.conv_k3(torch.ones(len(cs), 1), cs, 1, w, b))
+        assert _rel_err(got, ref) < 1e-6 and _rel_err(ops.join_h2(got_h), ref) < H2_TOL and int(flag.item()) == 0
+        only_h = ops.conv_k3_ones_from_parent(pnbr, keys, parent_of, info, w.to(DEV), b.to(DEV), relu=False, want_f32=False, want_h2=True)
+        assert only_h[0] is None and _rel_err(ops.join_h2(only_h[1]), S.conv_k3(torch.ones(len(cs), 1), cs, 1, w, b)) < H2_TOL
