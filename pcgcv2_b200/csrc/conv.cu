@@ -206,6 +206,7 @@ static bool rowlane_h2out_shape(int kind, int cin, int cout) {
     while ((1 << (log_lpr + 1)) <= lpr) ++log_lpr;
     while (((cout >> tz) & 1) == 0) ++tz;
     const int hs = log_lpr < tz ? log_lpr : tz;
+    if ((cout >> hs) == 1 && cout == lpr && cout % 4 == 0) return true;      // one channel per lane, lane l = channel l: quad gather
     return ((cout >> hs) % 2) == 0;
 }
 

@@ -44,7 +44,8 @@ static int launch_rowlane(const float *in, int in_ld, const int32_t *nbr, int64_
                           const float *res, int res_ld, float *out, int out_ld, int flags, cudaStream_t s,
                           uint32_t *oh = nullptr, int oh_ld = 0, int *ovf = nullptr) {
     using R = RowLane<CIN, COUT>;
-    if (oh && R::FC % 2 != 0) return kNotHandled;          // the h2 copy needs channel pairs per storing lane
+    // the h2 copy needs channel pairs per storing lane, or one channel per lane with lane l = channel l (quad gather, finish_row)
+    if (oh && R::FC % 2 != 0 && !(R::FC == 1 && COUT == R::LPR && COUT % 4 == 0)) return kNotHandled;
     const size_t smem = R::weight_smem_bytes(KVOL);
     auto kern = conv_rowlane_kernel<CIN, COUT, KVOL>;
     int rc = prepare_smem(kern, smem);

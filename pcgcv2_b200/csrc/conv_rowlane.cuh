@@ -140,7 +140,20 @@ __device__ __forceinline__ void finish_row(float (&acc)[COUT], int l, bool valid
         if (flags & PCGC_EPI_RELU) v = fmaxf(v, 0.f);
         acc[i] = v;
     }
-    if constexpr (R::FC % 2 == 0) {        // h2 copy for the next k=3 layer: 16-byte groups {hi01 hi23 lo01 lo23} (conv_h2.cuh)
+    if constexpr (R::FC == 1 && COUT == R::LPR && COUT % 4 == 0) {
+        // one finished channel per lane and lane l holds channel l (COUT == CIN / 4: conv1_0 of the InceptionResNet blocks):
+        // lane pairs form the (hi, lo) pairs, the lane two further on holds the other pair of the 16-byte group
+        if (out_h2) {                      // (uniform over the warp)
+            const float other = __shfl_xor_sync(0xffffffffu, acc[0], 1);
+            uint32_t hi, lo;
+            split_pair_h2(acc[0], other, hi, lo);                                  // meaningful on even lanes
+            const uint32_t phi = __shfl_xor_sync(0xffffffffu, hi, 2), plo = __shfl_xor_sync(0xffffffffu, lo, 2);
+            if (store) {
+                *over |= !(fabsf(acc[0]) <= kH2Limit);
+                if ((base & 3) == 0) *reinterpret_cast<uint4 *>(out_h2 + row * out_h2_ld + base) = make_uint4(hi, phi, lo, plo);
+            }
+        }
+    } else if constexpr (R::FC % 2 == 0) { // h2 copy for the next k=3 layer: 16-byte groups {hi01 hi23 lo01 lo23} (conv_h2.cuh)
         if (out_h2) {                      // (uniform over the warp)
             uint32_t *oh = out_h2 + row * out_h2_ld;
             if constexpr (R::FC % 4 == 0) {
