@@ -107,3 +107,23 @@ def test_range_coder_from_symbol_intervals_is_the_same_stream():
     got = ops.rc_encode_ranges(lo | ((hi - 1) << 16))
     assert got == ops.rc_encode_u16(tab, sym) == rangecoder_ref.encode_u16(tab, rows.astype(np.int32), flat)
     assert ops.rc_encode_ranges(np.zeros(0, np.uint32)) == ops.rc_encode_u16(tab, np.zeros((0, C), np.int16))
+
+
+def test_bench_algorithmic_bytes_match_the_survey():
+    """bench.py's section-8(d) byte model on SURVEY Appendix C's level sizes gives the survey's totals: 8.57 GB over the 106
+    convolutions of one encode + decode, 474.4 MB for decoder.conv2 (the roofline kernel)."""
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    n = {"L0": 795124, "L1": 211346, "L2": 54369, "L3": 13784, "U2": 110272, "U1": 434952, "U0": 1690768}
+    p = {"L0": 10403828, "L1": 2910160, "L2": 765843, "L3": 196102, "U2": 2137666, "U1": 8388378, "U0": 32243344}
+    convs, everything = bench.pass_algorithmic_bytes(n, p)
+    assert abs(convs - 8.569e9) < 0.01 * 8.569e9 and everything > convs
+    assert bench.k3_algorithmic_bytes(1690768, 32248086, 16, 16) == 474430640
