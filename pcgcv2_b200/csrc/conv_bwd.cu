@@ -248,9 +248,9 @@ static int launch_weight_grad(int mode, const float *A, int a_ld, const float *B
     if (ca % 4 == 0 && cb % 4 == 0 && nm >= 1 && nm <= 256) {     // register micro-tiles
         const size_t tile = sizeof(float) * kWgradTileRows * (ca + cb), red = sizeof(float) * (size_t)(256 / nm) * ca * cb;
         const size_t smem_mt = tile > red ? tile : red;
-        static bool opted = false;
-        if (!opted) { cudaFuncSetAttribute(weight_grad_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); opted = true; }
         PCGC_REQUIRE(smem_mt <= 96 * 1024, "weight gradient: %dx%d channels need too much shared memory", ca, cb);
+        if (smem_mt > 48 * 1024)                                  // per call: the attribute belongs to the current device's context
+            PCGC_CUDA(cudaFuncSetAttribute(weight_grad_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         weight_grad_mt_kernel<<<grid, 256, smem_mt, s>>>(mode, A, a_ld, B, b_ld, nbr, parent_of, keys, n, ca, cb, rows_per_block, part);
         int rc = check_launch("weight_grad_mt");
         if (rc) return rc;
