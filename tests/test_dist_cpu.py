@@ -27,16 +27,7 @@ def _worker(rank, world, port, q):
 
 
 def test_two_rank_counters_and_max_time():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted(q.get(timeout=120) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _spawn_two(_worker)
     assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3]                  # frame i -> rank i mod world
     for r in res:
         assert r[2] == [[1000, 77, 3], [2000, 78, 2]]                       # every rank sees every counter
@@ -81,18 +72,34 @@ def _bucket_worker(rank, world, port, q, overlap):
     dist.destroy_process_group()
 
 
+def _spawn_two(target, extra=(), attempts=3):
+    """two gloo ranks on a free port; a rendezvous that fails (the port was taken between probing and binding) is retried."""
+    last = None
+    for _ in range(attempts):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, 2, port, q) + tuple(extra)) for r in range(2)]
+        for p in procs:
+            p.start()
+        try:
+            res = sorted(q.get(timeout=180) for _ in procs)
+            for p in procs:
+                p.join(timeout=60)
+            if all(p.exitcode == 0 for p in procs):
+                return res
+            last = [p.exitcode for p in procs]
+        except Exception as e:                                   # queue.Empty: a rank died before reporting
+            last = e
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+            p.join(timeout=10)
+    raise AssertionError(f"two-rank run failed {attempts} times: {last}")
+
+
 def _run_bucket(overlap):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted(q.get(timeout=180) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    return res
+    return _spawn_two(_bucket_worker, (overlap,))
 
 
 def test_two_rank_gradient_buckets_average_and_keep_replicas_identical():
