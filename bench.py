@@ -218,11 +218,13 @@ def run_ours(args, rank, world, local_rank):
     dev_frames = [h.to(dev) for h in host_frames]
     host_coords, dev_coords = host_frames[0], dev_frames[0]
 
-    def step_device():                                       # inputs resident in HBM, result left on the device
-        return pipe.roundtrip(dev_frames, to_host=False)[0]
+    # k steps = k * depth frames handed to the pipeline in ONE call: the frames of consecutive steps follow each other through the
+    # workers without a drain / refill of the pipeline at every step boundary (the steady state of a stream of frames)
+    def step_device(k=1):                                    # inputs resident in HBM, result left on the device
+        return pipe.roundtrip(dev_frames * k, to_host=False)[0]
 
-    def step_e2e():                                          # public API with HOST buffers: H2D and D2H inside
-        return pipe.roundtrip(host_frames, to_host=True, copy=False)[0]
+    def step_e2e(k=1):                                       # public API with HOST buffers: H2D and D2H inside
+        return pipe.roundtrip(host_frames * k, to_host=True, copy=False)[0]
 
     def step_serial():                                       # one frame at a time on one stream (latency view)
         st = codec.encode(dev_coords)
@@ -233,13 +235,16 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, stream_steps=False):
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0, t0 = _lib.launch_count(), time.time()
         start.record()
-        for _ in range(steps):
-            last = fn()
+        if stream_steps:
+            last = fn(steps)
+        else:
+            for _ in range(steps):
+                last = fn()
         end.record()
         barrier()
         own = start.elapsed_time(end)
@@ -269,11 +274,11 @@ def run_ours(args, rank, world, local_rank):
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     codec.probe = {name: [] for name in probes}               # events on worker 0's stream, inside the timed region
-    ms_total, (st, out), launches, (t0, t1), ms_own = timed(step_device, args.steps)
+    ms_total, (st, out), launches, (t0, t1), ms_own = timed(step_device, args.steps, stream_steps=not args.step_barrier)
     probe_ms = {name: [a.elapsed_time(b) for a, b in ev] for name, ev in codec.probe.items()}
     codec.probe = {}
     clocks = sampler.stop(t0, t1) if sampler else None
-    ms_e2e, _, _, _, ms_e2e_own = timed(step_e2e, args.steps)
+    ms_e2e, _, _, _, ms_e2e_own = timed(step_e2e, args.steps, stream_steps=not args.step_barrier)
     codec.probe = {name: [] for name in probes}               # the same kernels with nothing else on the GPU
     ms_serial, _, _, _, _ = timed(step_serial, args.steps)
     probe_ms_serial = {name: [a.elapsed_time(b) for a, b in ev] for name, ev in codec.probe.items()}
@@ -325,6 +330,9 @@ def run_ours(args, rank, world, local_rank):
                    "frames_per_step": world * depth,
                    "parallelism": f"frames sharded over {world} GPU(s), {depth} frame(s) in flight per GPU (one host thread + "
                                   "CUDA stream each: the host range coder of one frame overlaps the kernels of the other)",
+                   "timed_region": ("every step's frames are awaited before the next step is submitted" if args.step_barrier else
+                                    f"the {args.steps} x {depth} frames per GPU of the timed steps are submitted as one stream of frames: no pipeline "
+                                    "drain between steps; barrier + synchronize on both sides of the region"),
                    "serial_ms_per_frame": round(ms_serial / args.steps, 3), "host_cpus": len(os.sched_getaffinity(0)),
                    "host_cores_per_rank": host_cores,
                    "arithmetic": "k=3 / k=2 layers: operands split into f16 hi + f16 lo (22 significand bits), products on the tensor "
@@ -450,6 +458,8 @@ def main():
     ap.add_argument("--workload", default="codec", choices=["codec", "train"],
                     help="codec = BASELINE's headline (default); train = the config-5 training step (tools/bench_train.py)")
     ap.add_argument("--batch", type=int, default=32, help="--workload train: samples per rank and step")
+    ap.add_argument("--step-barrier", action="store_true",
+                    help="wait for every step's frames before submitting the next step's (drains the pipeline at each step boundary)")
     ap.add_argument("--config3-frames", action="store_true",
                     help="N > 1: code config 3's four jittered clouds (every rank all four, rotated) instead of config 2's cloud in every slot")
     args = ap.parse_args()

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -90,6 +91,9 @@ class _FullOctets:
 
 
 _FULL = _FullOctets()            # "a full-octet level" for kernel-routing questions asked before the level exists
+
+
+_SPIN_LOCK = threading.Lock() if os.environ.get("PCGC_SYNC_LOCK", "0") == "1" else None
 
 
 class Codec:
@@ -588,7 +592,11 @@ class Codec:
         720.7 vs 855.7 on eight GPUs with 4 cores per rank (the wake-up through the interrupt path costs more than the spinning
         threads take from the enqueueing one)."""
         if not self._blocking_sync:
-            torch.cuda.current_stream().synchronize()
+            if _SPIN_LOCK is not None:                            # experiment: at most one thread of the process spins at a time
+                with _SPIN_LOCK:
+                    torch.cuda.current_stream().synchronize()
+            else:
+                torch.cuda.current_stream().synchronize()
             return
         ev = self._sync_event
         if ev is None:
