@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = ``--depth`` (default 4) point-cloud frames per GPU, each through one full ``Codec.encode`` +
+One "step" = ``--depth`` (default 4; 3 on hosts with fewer than 6 cores per rank) point-cloud frames per GPU, each through one full ``Codec.encode`` +
 ``Codec.decode`` (BASELINE.json config 2 stand-in: ``synthetic_vox10``, 795 124 occupied voxels, r3
 checkpoint, rho = 1), kept in flight together by ``pcgcv2_b200.pipeline.FramePipeline`` (one host thread +
 CUDA stream per frame, so the sequential host range coder of one frame overlaps the kernels of the
@@ -201,7 +201,7 @@ def run_ours(args, rank, world, local_rank):
     # --config3-frames: the four jittered clouds instead (seeds 0-3, radii +-10 %: 690-840 k voxels); the `depth` frames a rank
     # keeps in flight are clouds (rank + j) mod 4, so with depth 4 every rank codes all four each step and the ranks still
     # carry equal work (round 1 gave rank r cloud r only: the max-over-ranks time then measured the largest cloud).
-    depth = max(1, args.depth)
+    depth = args.depth if args.depth >= 1 else (4 if host_cores >= 6 else 3)
     args.same_frames = not args.config3_frames
     if world > 1 and not args.same_frames:
         clouds = [synth.synthetic_vox10(seed=s, jitter=0.1) for s in range(4)]
@@ -452,9 +452,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=4,
-                    help="frames in flight per GPU (1 = one frame at a time; measured on B200: 2 -> 96, 3 -> 108, 4 -> 112, 6 -> 115 "
-                         "Mpoints/s, profiles/r02_depth_sweep.txt)")
+    ap.add_argument("--depth", type=int, default=0,
+                    help="frames in flight per GPU (1 = one frame at a time); 0 = auto: 4 with 6 or more host cores per rank, else 3 "
+                         "(measured on B200 with the streamed timed region: 16 cores 3 -> 129, 4 -> 136, 6 -> 134 Mpoints/s; 4 cores "
+                         "3 -> 130, 4 -> 127, 6 -> 125; profiles/r02_scaling_host_experiments.txt)")
     ap.add_argument("--workload", default="codec", choices=["codec", "train"],
                     help="codec = BASELINE's headline (default); train = the config-5 training step (tools/bench_train.py)")
     ap.add_argument("--batch", type=int, default=32, help="--workload train: samples per rank and step")
